@@ -1,0 +1,483 @@
+// K1/K2/K7/K8: implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
+//
+//   out[row(m), n] = epilogue( sum_k A[m,k] * W[n,k] )        (aldm_gemm_desc, include/aldm_b200.h)
+//
+// Precision: fp32-faithful "bf16x3".  Activations arrive as two bf16 planes (x ~= hi + lo,
+// written by the prep kernels / producer epilogues) and weights are packed hi/lo the same way;
+// each K step issues three kind::f16 UMMAs (hi*hi, hi*lo, lo*hi) into one fp32 TMEM
+// accumulator, which restores ~2^-17 relative operand precision at 1/3 of the bf16 tensor rate
+// (plain bf16 misses the 1e-3 waveform tolerance by an order of magnitude).
+//
+// Structure of one CTA (192 threads, one 128 x BN output tile, optional split-K slice):
+//   warps 0-3  A producers: gather 16-byte chunks (8 channels of one tap of one pixel) with
+//              cp.async + zero fill into 128B-swizzled K-major tiles; completion is signalled
+//              on the stage's mbarrier (cp.async.mbarrier.arrive).  Afterwards the same warps
+//              run the epilogue (TMEM lane == tile row == threadIdx.x).
+//   warp 4     B producer: one elected lane issues a TMA bulk copy (cp.async.bulk) of the
+//              host-packed, pre-swizzled weight tile image (hi|lo) per stage.
+//   warp 5     allocates TMEM; one elected lane issues tcgen05.mma and commits stages.
+#include "common.cuh"
+
+namespace aldm {
+
+// ------------------------------------------------------------------------------------------
+// row decoding + epilogue shared by the tensor-core kernel, the SIMT checker and split-K
+// ------------------------------------------------------------------------------------------
+struct RowInfo {
+  int b, oh, ow;
+  bool valid;
+  long long orow;
+};
+
+__device__ __forceinline__ RowInfo decode_row(const aldm_gemm_desc& d, int m, int M) {
+  RowInfo r;
+  r.valid = m < M;
+  int mm = r.valid ? m : 0;
+  r.ow = mm % d.OW;
+  int t = mm / d.OW;
+  r.oh = t % d.OH;
+  r.b = t / d.OH;
+  r.orow = ((long long)r.b * d.OHF + (long long)r.oh * d.osy + d.ooy) * d.OWF + r.ow;
+  return r;
+}
+
+// v[0..cnt) are post-activation values for output columns [n0, n0+cnt) of row r.
+__device__ __forceinline__ void epi_finish(const aldm_gemm_desc& d, const RowInfo& r, int n0, int cnt, float* v,
+                                           int n_out) {
+  if (!r.valid) return;
+  if (n0 >= n_out) return;
+  if (n0 + cnt > n_out) cnt = n_out - n0;
+  if (d.res) {
+    const float* rp = d.res + r.orow * d.ld_res + n0;
+    for (int i = 0; i < cnt; ++i) v[i] += __ldg(rp + i);
+  }
+  if (d.alpha != 1.0f)
+    for (int i = 0; i < cnt; ++i) v[i] *= d.alpha;
+  if (d.out_mode == ALDM_OUT_F32) {
+    float* op = d.out + r.orow * d.ldo + n0;
+    if (d.accumulate)
+      for (int i = 0; i < cnt; ++i) v[i] += op[i];
+    if (cnt == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+      for (int i = 0; i < cnt; ++i) op[i] = v[i];
+    }
+  } else if (d.out_mode == ALDM_OUT_PLANES) {
+    __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + r.orow * d.ldo + n0;
+    __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + r.orow * d.ldo + n0;
+    if (cnt == 32 && ((reinterpret_cast<uintptr_t>(hp) & 15u) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 h, l;
+        split8(v + i, h, l);
+        *reinterpret_cast<uint4*>(hp + i) = h;
+        *reinterpret_cast<uint4*>(lp + i) = l;
+      }
+    } else {
+      for (int i = 0; i < cnt; ++i) {
+        __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+        hp[i] = h;
+        lp[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+      }
+    }
+  } else {  // NCHW
+    for (int i = 0; i < cnt; ++i)
+      d.out[(((long long)r.b * d.N + (n0 + i)) * d.OH + r.oh) * d.OW + r.ow] = v[i];
+  }
+}
+
+// Bias / rowvec / activation for one 32-column chunk whose packed column base is pc0.
+// For GEGLU `g` holds the gate chunk (packed columns pc0 + bn/2 ...).
+__device__ __forceinline__ void epi_activate(const aldm_gemm_desc& d, const RowInfo& r, int pc0, float* v, float* g) {
+  if (d.bias) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __ldg(d.bias + pc0 + i);
+    if (d.act == ALDM_ACT_GEGLU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[i] += __ldg(d.bias + pc0 + d.bn / 2 + i);
+    }
+  }
+  if (d.rowvec) {
+    const float* rv = d.rowvec + (long long)r.b * d.ld_rowvec + pc0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __ldg(rv + i);
+  }
+  if (d.act == ALDM_ACT_GEGLU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= gelu_f(g[i]);
+  } else if (d.act == ALDM_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+  } else if (d.act == ALDM_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tensor-core kernel
+// ------------------------------------------------------------------------------------------
+template <int BN>
+struct TcCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;                       // bf16 elements = 128 bytes per row
+  static constexpr int A_BYTES = BM * 128;            // one plane
+  static constexpr int B_BYTES = BN * 128;            // one plane
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN;                // power of two >= 32
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ aldm_gemm_desc d) {
+  using C = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int M = d.B * d.OH * d.OW;
+  const int m0 = blockIdx.x * C::BM;
+  const int ntile = blockIdx.y;
+  const int nkb_total = d.Kpad / C::BK;
+  const int kb_begin = (int)(((long long)blockIdx.z * nkb_total) / d.splitk);
+  const int kb_end = (int)(((long long)(blockIdx.z + 1) * nkb_total) / d.splitk);
+  const int nkb = kb_end - kb_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 128 + 1);   // 128 cp.async producers + 1 expect_tx arrive
+      mbar_init(empty_bar(s), 1);        // tcgen05.commit
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    // ===================== A producers =====================
+    const int j = tid & 7;                 // 16-byte chunk (8 channels) inside the 64-wide K block
+    const int rbase = tid >> 3;            // rows rbase + 16*i
+    const uint32_t swz = (uint32_t)((j ^ (rbase & 7)) << 4);
+    int ih0[8], iw0[8], pb[8];             // pb < 0 => row out of range
+    const int Hs = d.H >> d.up, Ws = d.W >> d.up;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m = m0 + rbase + 16 * i;
+      if (m < M) {
+        int ow = m % d.OW;
+        int t = m / d.OW;
+        int oh = t % d.OH;
+        int b = t / d.OH;
+        ih0[i] = oh * d.sy;
+        iw0[i] = ow * d.sx;
+        pb[i] = (d.bmod > 0 ? b % d.bmod : b) * Hs;
+      } else {
+        ih0[i] = 0; iw0[i] = 0; pb[i] = -1;
+      }
+    }
+    const __nv_bfloat16* ahi = reinterpret_cast<const __nv_bfloat16*>(d.a_hi);
+    const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(d.a_lo);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % C::STAGES;
+      mbar_wait(empty_bar(s), ((it / C::STAGES) & 1) ^ 1);
+      const int k = (kb_begin + it) * C::BK + j * 8;
+      const bool kvalid = k < d.K;
+      int tap = 0, c = 0;
+      if (kvalid) { tap = k / d.Cp; c = k - tap * d.Cp; }
+      const int dy = d.dy[tap], dx = d.dx[tap];
+      const uint32_t sa = base + s * C::STAGE_BYTES + swz;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ih = ih0[i] + dy, iw = iw0[i] + dx;
+        const bool ok = kvalid && pb[i] >= 0 && ih >= 0 && ih < d.H && iw >= 0 && iw < d.W;
+        long long off = 0;
+        if (ok) off = ((long long)(pb[i] + (ih >> d.up)) * Ws + (iw >> d.up)) * d.Cp + c;
+        const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
+        cp_async_16(dst, ahi + off, ok ? 16u : 0u);
+        cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive_noinc(full_bar(s));
+    }
+
+    // ===================== epilogue =====================
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m = m0 + tid;
+    const RowInfo r = decode_row(d, m, M);
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (d.splitk > 1) {
+      const int Mpad = gridDim.x * C::BM, Npad = gridDim.y * BN;
+      float* wp = d.ws + ((long long)blockIdx.z * Mpad + m) * Npad + ntile * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(wp + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else if (d.act == ALDM_ACT_GEGLU) {
+      const int n_out = d.N / 2;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+        uint32_t vr[32], gr[32];
+        tmem_ld32(trow + c0, vr);
+        tmem_ld32(trow + BN / 2 + c0, gr);
+        tmem_ld_wait();
+        float* v = reinterpret_cast<float*>(vr);
+        float* g = reinterpret_cast<float*>(gr);
+        epi_activate(d, r, ntile * BN + c0, v, g);
+        epi_finish(d, r, ntile * (BN / 2) + c0, 32, v, n_out);
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t vr[32];
+        tmem_ld32(trow + c0, vr);
+        tmem_ld_wait();
+        float* v = reinterpret_cast<float*>(vr);
+        epi_activate(d, r, ntile * BN + c0, v, nullptr);
+        epi_finish(d, r, ntile * BN + c0, 32, v, d.N);
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== B producer (TMA bulk copy of packed tile images) =====================
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(d.w_packed) +
+                            ((long long)ntile * nkb_total + kb_begin) * (2 * C::B_BYTES);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(empty_bar(s), ((it / C::STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
+        bulk_g2s(base + s * C::STAGE_BYTES + 2 * C::A_BYTES, wsrc + (long long)it * (2 * C::B_BYTES),
+                 2 * C::B_BYTES, full_bar(s));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(full_bar(s), (it / C::STAGES) & 1);
+        tc_fence_after();
+        fence_proxy_async();
+        const uint32_t sa = base + s * C::STAGE_BYTES;
+        const uint64_t da_hi = umma_desc_sw128(sa);
+        const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);
+        const uint64_t db_hi = umma_desc_sw128(sa + 2 * C::A_BYTES);
+        const uint64_t db_lo = umma_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {            // 4 x K=16 (32 bytes) inside the 128B swizzle row
+          const uint64_t o = (uint64_t)(ks * 2);    // +32 bytes in the (addr >> 4) field
+          umma_bf16(tmem_base, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
+          umma_bf16(tmem_base, da_hi + o, db_lo + o, idesc, 1);
+          umma_bf16(tmem_base, da_hi + o, db_hi + o, idesc, 1);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// split-K reduction + epilogue
+// ------------------------------------------------------------------------------------------
+__global__ void splitk_epilogue_kernel(const __grid_constant__ aldm_gemm_desc d, int Mpad, int Npad) {
+  const int M = d.B * d.OH * d.OW;
+  const int chunks_per_row = (d.act == ALDM_ACT_GEGLU) ? (Npad / d.bn) * (d.bn / 64) : Npad / 32;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * chunks_per_row) return;
+  const int m = (int)(idx / chunks_per_row);
+  const int ch = (int)(idx % chunks_per_row);
+  const RowInfo r = decode_row(d, m, M);
+  float v[32], g[32];
+  int pc0, n0, n_out;
+  if (d.act == ALDM_ACT_GEGLU) {
+    const int per_tile = d.bn / 64;
+    const int tile = ch / per_tile, sub = ch % per_tile;
+    pc0 = tile * d.bn + sub * 32;
+    n0 = tile * (d.bn / 2) + sub * 32;
+    n_out = d.N / 2;
+  } else {
+    pc0 = ch * 32; n0 = pc0; n_out = d.N;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { v[i] = 0.f; g[i] = 0.f; }
+  for (int z = 0; z < d.splitk; ++z) {
+    const float* wp = d.ws + ((long long)z * Mpad + m) * Npad + pc0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 t = *reinterpret_cast<const float4*>(wp + i);
+      v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+    }
+    if (d.act == ALDM_ACT_GEGLU) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(wp + d.bn / 2 + i);
+        g[i] += t.x; g[i + 1] += t.y; g[i + 2] += t.z; g[i + 3] += t.w;
+      }
+    }
+  }
+  epi_activate(d, r, pc0, v, g);
+  epi_finish(d, r, n0, 32, v, n_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT checker: obviously-correct restatement of the same descriptor on CUDA cores (fp32 FMA).
+// One warp per output row, lanes over 32 packed columns.  Validation / debugging only.
+// ------------------------------------------------------------------------------------------
+__global__ void gemm_simt_kernel(const __grid_constant__ aldm_gemm_desc d, int Npad) {
+  const int M = d.B * d.OH * d.OW;
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const RowInfo r = decode_row(d, m, M);
+  const int Hs = d.H >> d.up, Ws = d.W >> d.up;
+  const int bsrc = d.bmod > 0 ? r.b % d.bmod : r.b;
+  const __nv_bfloat16* ahi = reinterpret_cast<const __nv_bfloat16*>(d.a_hi);
+  const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(d.a_lo);
+  const bool geglu = d.act == ALDM_ACT_GEGLU;
+  const int nchunks = geglu ? (Npad / d.bn) * (d.bn / 64) : Npad / 32;
+  for (int ch = blockIdx.y; ch < nchunks; ch += gridDim.y) {
+    int pc0, n0, n_out;
+    if (geglu) {
+      const int per_tile = d.bn / 64;
+      const int tile = ch / per_tile, sub = ch % per_tile;
+      pc0 = tile * d.bn + sub * 32; n0 = tile * (d.bn / 2) + sub * 32; n_out = d.N / 2;
+    } else {
+      pc0 = ch * 32; n0 = pc0; n_out = d.N;
+    }
+    const float* wv = d.w_plain + (long long)(pc0 + lane) * d.Kpad;
+    const float* wg = wv + (long long)(d.bn / 2) * d.Kpad;
+    float acc = 0.f, accg = 0.f;
+    for (int tap = 0; tap < d.ntaps; ++tap) {
+      const int ih = r.oh * d.sy + d.dy[tap], iw = r.ow * d.sx + d.dx[tap];
+      if (ih < 0 || ih >= d.H || iw < 0 || iw >= d.W) continue;
+      const long long off = ((long long)(bsrc * Hs + (ih >> d.up)) * Ws + (iw >> d.up)) * d.Cp;
+      const float* wt = wv + tap * d.Cp;
+      const float* wgt = wg + tap * d.Cp;
+      for (int c = 0; c < d.Cp; ++c) {
+        const float a = __bfloat162float(ahi[off + c]) + __bfloat162float(alo[off + c]);
+        acc = fmaf(a, __ldg(wt + c), acc);
+        if (geglu) accg = fmaf(a, __ldg(wgt + c), accg);
+      }
+    }
+    // gather the 32 lanes' results into every lane's registers via shuffles, lane 0.. stores
+    float v[32], g[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = __shfl_sync(0xffffffffu, acc, i);
+      g[i] = __shfl_sync(0xffffffffu, accg, i);
+    }
+    if (lane == 0) {
+      epi_activate(d, r, pc0, v, g);
+      epi_finish(d, r, n0, 32, v, n_out);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host launch
+// ------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_tc(const aldm_gemm_desc& d, int M, cudaStream_t st) {
+  using C = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(cdiv(M, C::BM), cdiv(d.N, BN), d.splitk);
+  gemm_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, st>>>(d);
+  ALDM_CHECK_CUDA(cudaGetLastError());
+  if (d.splitk > 1) {
+    const int Mpad = grid.x * C::BM, Npad = grid.y * BN;
+    const int chunks = (d.act == ALDM_ACT_GEGLU) ? (Npad / BN) * (BN / 64) : Npad / 32;
+    const long long total = (long long)M * chunks;
+    splitk_epilogue_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d, Mpad, Npad);
+    ALDM_CHECK_CUDA(cudaGetLastError());
+  }
+  return ALDM_OK;
+}
+
+int gemm_num_launches(const aldm_gemm_desc& d) { return (d.impl == ALDM_GEMM_TC && d.splitk > 1) ? 2 : 1; }
+
+int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
+  const long long Mll = (long long)d.B * d.OH * d.OW;
+  ALDM_REQUIRE(Mll > 0 && Mll < (1ll << 31), ALDM_E_SHAPE, "gemm: bad M=%lld", Mll);
+  const int M = (int)Mll;
+  ALDM_REQUIRE(d.bn == 32 || d.bn == 64 || d.bn == 128, ALDM_E_UNSUPPORTED, "gemm: bn=%d unsupported", d.bn);
+  ALDM_REQUIRE(d.Cp % 8 == 0 && d.Cp > 0, ALDM_E_SHAPE, "gemm: Cp=%d must be a positive multiple of 8", d.Cp);
+  ALDM_REQUIRE(d.ntaps >= 1 && d.ntaps <= ALDM_MAX_TAPS, ALDM_E_SHAPE, "gemm: ntaps=%d", d.ntaps);
+  ALDM_REQUIRE(d.K == d.ntaps * d.Cp, ALDM_E_SHAPE, "gemm: K=%d != ntaps*Cp=%d", d.K, d.ntaps * d.Cp);
+  ALDM_REQUIRE(d.Kpad % 64 == 0 && d.Kpad >= d.K, ALDM_E_SHAPE, "gemm: Kpad=%d (K=%d)", d.Kpad, d.K);
+  ALDM_REQUIRE(d.N >= 1, ALDM_E_SHAPE, "gemm: N=%d", d.N);
+  ALDM_REQUIRE(d.a_hi && d.a_lo, ALDM_E_ARG, "gemm: null A planes");
+  ALDM_REQUIRE(aligned16(d.a_hi) && aligned16(d.a_lo), ALDM_E_ALIGN, "gemm: A planes not 16B aligned");
+  ALDM_REQUIRE(d.up == 0 || d.up == 1, ALDM_E_ARG, "gemm: up=%d", d.up);
+  ALDM_REQUIRE(d.splitk >= 1 && d.splitk <= d.Kpad / 64, ALDM_E_ARG, "gemm: splitk=%d", d.splitk);
+  ALDM_REQUIRE(d.splitk == 1 || d.ws, ALDM_E_ARG, "gemm: split-K needs a workspace");
+  if (d.act == ALDM_ACT_GEGLU) {
+    ALDM_REQUIRE(d.bn >= 64 && d.N % d.bn == 0, ALDM_E_SHAPE, "gemm: GEGLU needs N %% bn == 0 and bn >= 64");
+    ALDM_REQUIRE(!d.rowvec, ALDM_E_UNSUPPORTED, "gemm: GEGLU with rowvec");
+  }
+  if (d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_NCHW) {
+    ALDM_REQUIRE(d.out, ALDM_E_ARG, "gemm: null out");
+  } else {
+    ALDM_REQUIRE(d.out_hi && d.out_lo, ALDM_E_ARG, "gemm: null out planes");
+    ALDM_REQUIRE(!d.accumulate, ALDM_E_UNSUPPORTED, "gemm: accumulate into planes");
+  }
+  if (d.impl == ALDM_GEMM_SIMT) {
+    ALDM_REQUIRE(d.w_plain, ALDM_E_ARG, "gemm: SIMT path needs w_plain");
+    const int Npad = cdiv(d.N, d.bn) * d.bn;
+    const bool geglu = d.act == ALDM_ACT_GEGLU;
+    const int nchunks = geglu ? (Npad / d.bn) * (d.bn / 64) : Npad / 32;
+    dim3 grid(cdiv(M, 4), nchunks < 64 ? nchunks : 64);
+    gemm_simt_kernel<<<grid, 128, 0, st>>>(d, Npad);
+    ALDM_CHECK_CUDA(cudaGetLastError());
+    return ALDM_OK;
+  }
+  ALDM_REQUIRE(d.w_packed && aligned16(d.w_packed), ALDM_E_ARG, "gemm: w_packed null/unaligned");
+  switch (d.bn) {
+    case 128: return launch_tc<128>(d, M, st);
+    case 64: return launch_tc<64>(d, M, st);
+    default: return launch_tc<32>(d, M, st);
+  }
+}
+
+}  // namespace aldm
+
+extern "C" int aldm_gemm(const aldm_gemm_desc* d, void* stream) {
+  if (!d) { aldm::set_error("aldm_gemm: null desc"); return ALDM_E_ARG; }
+  return aldm::gemm_launch(*d, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,301 @@
+// K3: operand preparation -- GroupNorm / LayerNorm / SiLU / leaky-ReLU applied once per tensor and
+// written as the two bf16 planes (hi, lo) the tensor-core GEMM consumes.  All kernels are
+// HBM/L2-bound streaming kernels: float4 loads, 8/16-byte stores, warp-shuffle reductions.
+//
+//   GN  : gn_stats_kernel  (per-block fp32 partial sums -> double partials, no atomics, deterministic)
+//         gn_apply_kernel  (reduces the partials for its batch row, builds per-channel scale/shift
+//                           in shared memory, applies (+SiLU), splits, stores)
+//   LN  : ln_kernel        (one warp per token row, two-pass statistics in registers)
+//   misc: ew_kernel        (copy / SiLU / leaky-ReLU, optional concat of two sources, NCHW source)
+//         pack_b_kernel    (fp32 matrix -> swizzled hi/lo weight tile images, for dynamic B operands)
+#include "common.cuh"
+
+namespace aldm {
+
+static constexpr int GN_MAX_BLOCKS = 64;   // partial-sum blocks per batch row
+static constexpr int GN_MAX_C = 2048;
+
+__device__ __forceinline__ float4 load_cat4(const aldm_prep_desc& d, long long row, int c) {
+  // 4 consecutive channels starting at c (c % 4 == 0) of the concatenated tensor; c0 % 4 == 0
+  if (c < d.c0) return *reinterpret_cast<const float4*>(d.src0 + row * d.c0 + c);
+  return *reinterpret_cast<const float4*>(d.src1 + row * d.c1 + (c - d.c0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics: grid (nblk, B); block 256.  partial[b][blk][g] = (sum, sumsq) as doubles.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __grid_constant__ aldm_prep_desc d, int nblk) {
+  __shared__ double s_sum[32], s_sq[32];
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int C = d.c0 + d.c1, Q = C >> 2, cpg = C / d.groups;
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int rows_per = (d.HW + nblk - 1) / nblk;
+  const int r0 = blk * rows_per;
+  const int r1 = min(d.HW, r0 + rows_per);
+  const long long total = (long long)max(0, r1 - r0) * Q;
+  float acc = 0.f, acc2 = 0.f;
+  int cur_g = -1;
+  for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pr = (int)(idx / Q), q = (int)(idx % Q);
+    const long long row = (long long)b * d.HW + r0 + pr;
+    const float4 v = load_cat4(d, row, q * 4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (q * 4 + e) / cpg;
+      if (g != cur_g) {
+        if (cur_g >= 0) { atomicAdd(&s_sum[cur_g], (double)acc); atomicAdd(&s_sq[cur_g], (double)acc2); }
+        cur_g = g; acc = 0.f; acc2 = 0.f;
+      }
+      acc += vv[e];
+      acc2 = fmaf(vv[e], vv[e], acc2);
+    }
+  }
+  if (cur_g >= 0) { atomicAdd(&s_sum[cur_g], (double)acc); atomicAdd(&s_sq[cur_g], (double)acc2); }
+  __syncthreads();
+  if (threadIdx.x < d.groups) {
+    double* p = d.scratch + (((long long)b * nblk + blk) * d.groups + threadIdx.x) * 2;
+    p[0] = s_sum[threadIdx.x];
+    p[1] = s_sq[threadIdx.x];
+  }
+}
+
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hp, __nv_bfloat16* lp, const float* y) {
+  uint2 h, l;
+  split2(y[0], y[1], h.x, l.x);
+  split2(y[2], y[3], h.y, l.y);
+  *reinterpret_cast<uint2*>(hp) = h;
+  *reinterpret_cast<uint2*>(lp) = l;
+}
+
+// grid (nblk_apply, B); block 256
+__global__ void gn_apply_kernel(const __grid_constant__ aldm_prep_desc d, int nblk_stats) {
+  __shared__ float s_scale[GN_MAX_C], s_shift[GN_MAX_C];
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.y;
+  const int C = d.c0 + d.c1, Q = C >> 2, cpg = C / d.groups;
+  if (threadIdx.x < d.groups) {
+    double s = 0.0, s2 = 0.0;
+    for (int k = 0; k < nblk_stats; ++k) {
+      const double* p = d.scratch + (((long long)b * nblk_stats + k) * d.groups + threadIdx.x) * 2;
+      s += p[0]; s2 += p[1];
+    }
+    const double n = (double)d.HW * cpg;
+    const double mean = s / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)d.eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * __ldg(d.gamma + c);
+    s_scale[c] = sc;
+    s_shift[c] = __ldg(d.beta + c) - s_mean[g] * sc;
+  }
+  __syncthreads();
+  const int rows_per = (d.HW + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per;
+  const int r1 = min(d.HW, r0 + rows_per);
+  const long long total = (long long)max(0, r1 - r0) * Q;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+  const bool act = d.mode == ALDM_PREP_GN_SILU;
+  for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pr = (int)(idx / Q), q = (int)(idx % Q);
+    const long long row = (long long)b * d.HW + r0 + pr;
+    const float4 v = load_cat4(d, row, q * 4);
+    float y[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      y[e] = fmaf(y[e], s_scale[q * 4 + e], s_shift[q * 4 + e]);
+      if (act) y[e] = silu_f(y[e]);
+    }
+    store_planes4(hi + row * d.Cp + q * 4, lo + row * d.Cp + q * 4, y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, C % 4 == 0, C <= 1024
+// ---------------------------------------------------------------------------------------------
+__global__ void ln_kernel(const __grid_constant__ aldm_prep_desc d) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= d.rows) return;
+  const int C = d.c0, Q = C >> 2;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int q = lane + 32 * i;
+    if (q < Q) {
+      v[i] = *reinterpret_cast<const float4*>(d.src0 + row * C + q * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int q = lane + 32 * i;
+    if (q < Q) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      s2 += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const float rstd = rsqrtf(s2 / C + d.eps);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int q = lane + 32 * i;
+    if (q < Q) {
+      const float4 g = *reinterpret_cast<const float4*>(d.gamma + q * 4);
+      const float4 be = *reinterpret_cast<const float4*>(d.beta + q * 4);
+      float y[4];
+      y[0] = (v[i].x - mean) * rstd * g.x + be.x;
+      y[1] = (v[i].y - mean) * rstd * g.y + be.y;
+      y[2] = (v[i].z - mean) * rstd * g.z + be.z;
+      y[3] = (v[i].w - mean) * rstd * g.w + be.w;
+      store_planes4(hi + row * d.Cp + q * 4, lo + row * d.Cp + q * 4, y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise copy / SiLU / leaky-ReLU -> planes; one thread per (row, 8-channel chunk)
+// ---------------------------------------------------------------------------------------------
+__global__ void ew_kernel(const __grid_constant__ aldm_prep_desc d) {
+  const int C = d.c0 + d.c1;
+  const int chunks = d.Cp >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)d.rows * chunks) return;
+  const long long row = idx / chunks;
+  const int c = (int)(idx % chunks) * 8;
+  float y[8];
+  if (d.src_nchw) {
+    const long long b = row / d.HW, p = row % d.HW;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = (c + e < C) ? __ldg(d.src0 + (b * C + c + e) * d.HW + p) : 0.f;
+  } else if (c + 8 <= C && (d.c0 % 8 == 0) && (d.c1 % 4 == 0)) {
+    const float4 a = load_cat4(d, row, c), bb = load_cat4(d, row, c + 4);
+    y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = bb.x; y[5] = bb.y; y[6] = bb.z; y[7] = bb.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int cc = c + e;
+      y[e] = cc < d.c0 ? d.src0[row * d.c0 + cc] : (cc < C ? d.src1[row * d.c1 + cc - d.c0] : 0.f);
+    }
+  }
+  if (d.mode == ALDM_PREP_SILU) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = silu_f(y[e]);
+  } else if (d.mode == ALDM_PREP_LRELU) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = y[e] > 0.f ? y[e] : y[e] * d.slope;
+  }
+  uint4 h, l;
+  split8(y, h, l);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + row * d.Cp + c) = h;
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + row * d.Cp + c) = l;
+}
+
+int prep_num_launches(const aldm_prep_desc& d) {
+  return (d.mode == ALDM_PREP_GN || d.mode == ALDM_PREP_GN_SILU) ? 2 : 1;
+}
+
+int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
+  ALDM_REQUIRE(d.src0 && d.out_hi && d.out_lo, ALDM_E_ARG, "prep: null pointer");
+  ALDM_REQUIRE(d.rows > 0 && d.c0 > 0 && d.c1 >= 0, ALDM_E_SHAPE, "prep: rows=%d c0=%d c1=%d", d.rows, d.c0, d.c1);
+  const int C = d.c0 + d.c1;
+  ALDM_REQUIRE(d.Cp % 8 == 0 && d.Cp >= C && d.Cp < C + 8, ALDM_E_SHAPE, "prep: Cp=%d for C=%d", d.Cp, C);
+  ALDM_REQUIRE(aligned16(d.src0) && aligned16(d.out_hi) && aligned16(d.out_lo), ALDM_E_ALIGN, "prep: alignment");
+  if (d.mode == ALDM_PREP_GN || d.mode == ALDM_PREP_GN_SILU) {
+    ALDM_REQUIRE(d.gamma && d.beta && d.scratch, ALDM_E_ARG, "prep GN: null gamma/beta/scratch");
+    ALDM_REQUIRE(d.groups == 32 && C % d.groups == 0 && C <= GN_MAX_C, ALDM_E_UNSUPPORTED, "prep GN: C=%d groups=%d", C, d.groups);
+    ALDM_REQUIRE(C % 4 == 0 && d.c0 % 4 == 0 && d.Cp == C, ALDM_E_SHAPE, "prep GN: channels must be multiples of 4/8");
+    ALDM_REQUIRE(d.rows == d.B * d.HW, ALDM_E_SHAPE, "prep GN: rows != B*HW");
+    ALDM_REQUIRE(!d.src_nchw, ALDM_E_UNSUPPORTED, "prep GN: NCHW source");
+    int nblk = cdiv(d.HW, 32);
+    if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;
+    gn_stats_kernel<<<dim3(nblk, d.B), 256, 0, st>>>(d, nblk);
+    ALDM_CHECK_CUDA(cudaGetLastError());
+    int nap = cdiv(d.HW, 16);
+    if (nap > 128) nap = 128;
+    gn_apply_kernel<<<dim3(nap, d.B), 256, 0, st>>>(d, nblk);
+    ALDM_CHECK_CUDA(cudaGetLastError());
+  } else if (d.mode == ALDM_PREP_LN) {
+    ALDM_REQUIRE(d.gamma && d.beta, ALDM_E_ARG, "prep LN: null gamma/beta");
+    ALDM_REQUIRE(d.c1 == 0 && C % 4 == 0 && C <= 1024 && d.Cp == C, ALDM_E_UNSUPPORTED, "prep LN: C=%d", C);
+    ln_kernel<<<cdiv(d.rows, 8), 256, 0, st>>>(d);
+    ALDM_CHECK_CUDA(cudaGetLastError());
+  } else {
+    ALDM_REQUIRE(d.mode == ALDM_PREP_COPY || d.mode == ALDM_PREP_SILU || d.mode == ALDM_PREP_LRELU, ALDM_E_ARG,
+                 "prep: mode=%d", d.mode);
+    if (d.src_nchw) ALDM_REQUIRE(d.c1 == 0 && d.HW > 0 && d.rows % d.HW == 0, ALDM_E_SHAPE, "prep: NCHW source shape");
+    const long long total = (long long)d.rows * (d.Cp >> 3);
+    ew_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d);
+    ALDM_CHECK_CUDA(cudaGetLastError());
+  }
+  return ALDM_OK;
+}
+
+size_t gn_scratch_doubles(int B) { return (size_t)B * GN_MAX_BLOCKS * 32 * 2; }
+
+// ---------------------------------------------------------------------------------------------
+// pack_b: fp32 [N,K] (or its transpose) -> tile images  [n_tile][k_blk][hi|lo][bn rows][128 B swizzled]
+//         and (optionally) a plain fp32 [Npad, Kpad] copy for the SIMT checker.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_b_kernel(const float* __restrict__ src, int lds, int transpose, int N, int K, int bn,
+                              int Kpad, int Npad, uint8_t* __restrict__ dst, float* __restrict__ plain) {
+  const int chunks = Kpad >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Npad * chunks) return;
+  const int n = (int)(idx / chunks);
+  const int k0 = (int)(idx % chunks) * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    v[e] = (n < N && k < K) ? (transpose ? src[(long long)k * lds + n] : src[(long long)n * lds + k]) : 0.f;
+  }
+  if (plain) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) plain[(long long)n * Kpad + k0 + e] = v[e];
+  }
+  uint4 h, l;
+  split8(v, h, l);
+  const int tile = n / bn, r = n % bn, kb = k0 >> 6, j = (k0 & 63) >> 3;
+  const long long tile_bytes = (long long)bn * 128;
+  uint8_t* base = dst + ((long long)tile * (Kpad >> 6) + kb) * (2 * tile_bytes);
+  const int off = r * 128 + ((j ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(base + off) = h;
+  *reinterpret_cast<uint4*>(base + tile_bytes + off) = l;
+}
+
+}  // namespace aldm
+
+extern "C" int aldm_prep(const aldm_prep_desc* d, void* stream) {
+  if (!d) { aldm::set_error("aldm_prep: null desc"); return ALDM_E_ARG; }
+  return aldm::prep_launch(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int aldm_pack_b(const float* src, int32_t lds, int32_t transpose, int32_t N, int32_t K, int32_t bn,
+                           void* dst_packed, float* dst_plain, void* stream) {
+  using namespace aldm;
+  ALDM_REQUIRE(src && dst_packed, ALDM_E_ARG, "pack_b: null pointer");
+  ALDM_REQUIRE(bn == 32 || bn == 64 || bn == 128, ALDM_E_UNSUPPORTED, "pack_b: bn=%d", bn);
+  ALDM_REQUIRE(N > 0 && K > 0, ALDM_E_SHAPE, "pack_b: N=%d K=%d", N, K);
+  const int Kpad = cdiv(K, 64) * 64, Npad = cdiv(N, bn) * bn;
+  const long long total = (long long)Npad * (Kpad >> 3);
+  pack_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, lds, transpose, N, K, bn, Kpad, Npad, reinterpret_cast<uint8_t*>(dst_packed), dst_plain);
+  ALDM_CHECK_CUDA(cudaGetLastError());
+  return ALDM_OK;
+}
