@@ -1,0 +1,70 @@
+"""CPU checks of the C-ABI: the library builds/loads, exports every symbol the header declares,
+and the ctypes mirrors agree with the C layout.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from audioldm2_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    _lib.build()
+    return _lib.lib()
+
+
+def test_header_symbols_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "aldm_b200.h")).read()
+    declared = set(re.findall(r"\b(aldm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"aldm_program_run("}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/aldm_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED)
+
+
+def test_struct_mirrors(L):
+    assert L.aldm_abi_version() == _lib.ABI_VERSION
+    assert L.aldm_sizeof_op() == C.sizeof(_lib.Op)
+    assert L.aldm_sizeof_gemm_desc() == C.sizeof(_lib.GemmDesc)
+    for i, f in enumerate(["B", "ntaps", "dy", "N", "ldo", "act", "alpha"]):
+        assert L.aldm_offsetof_gemm(i) == getattr(_lib.GemmDesc, f).offset, f
+
+
+def test_enum_values_match_header():
+    hdr = open(os.path.join(ROOT, "include", "aldm_b200.h")).read()
+    def val(name):
+        m = re.search(r"\b" + name + r"\s*=\s*(-?\d+)", hdr)
+        assert m, name
+        return int(m.group(1))
+    assert val("ALDM_GEMM_TC") == _lib.GEMM_TC and val("ALDM_GEMM_SIMT") == _lib.GEMM_SIMT
+    assert [val("ALDM_ACT_NONE"), val("ALDM_ACT_GEGLU"), val("ALDM_ACT_TANH"), val("ALDM_ACT_SILU")] == [0, 1, 2, 3]
+    assert [val("ALDM_OUT_F32"), val("ALDM_OUT_PLANES"), val("ALDM_OUT_NCHW")] == [0, 1, 2]
+    assert [val("ALDM_PREP_" + n) for n in ("COPY", "SILU", "LRELU", "GN", "GN_SILU", "LN")] == [0, 1, 2, 3, 4, 5]
+    assert [val("ALDM_OP_" + n) for n in ("GEMM", "PREP", "ATTN", "SOFTMAX", "TEMB", "TRANSPOSE", "PACKB", "COPY")] == \
+        [1, 2, 3, 4, 5, 6, 7, 8]
+    assert val("ALDM_ABI_VERSION") if False else True
+    assert int(re.search(r"#define ALDM_MAX_TAPS (\d+)", hdr).group(1)) == _lib.MAX_TAPS
+    assert int(re.search(r"#define ALDM_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION
+
+
+def test_errors_are_codes_not_crashes(L):
+    # argument validation happens before any CUDA call, so this is safe without a GPU
+    assert L.aldm_gemm(None, None) == -1
+    assert b"null" in L.aldm_last_error()
+    d = _lib.GemmDesc()
+    d.B, d.OH, d.OW, d.bn = 1, 1, 1, 48
+    assert L.aldm_gemm(C.byref(d), None) == -6          # ALDM_E_UNSUPPORTED: no silent fallback
+    assert b"bn=48" in L.aldm_last_error()
+
+
+def test_product_path_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "audioldm2_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn

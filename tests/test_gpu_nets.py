@@ -1,0 +1,141 @@
+"""GPU parity tests of whole networks and of the sampler, through the native engine (C-ABI), against
+(a) the committed golden fixtures = outputs of the unmodified reference modules, and
+(b) the CPU oracle on the same seeded inputs.
+
+Tolerances: single network evaluation 1e-4 relative L2 (measured ~1e-5: operand planes carry
+2^-17 relative error, accumulation is fp32); end-to-end waveform after 10 / 200 DDIM steps 1e-3
+relative L2 -- the tolerance BASELINE.json's north_star states."""
+import pytest
+import torch
+
+from audioldm2_b200 import arch, model, synth
+from tests.conftest import rel_l2
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NET_TOL = 1e-4
+WAVE_TOL = 1e-3
+
+
+def _to(c, dev):
+    return dict(context_list=[t.to(dev) for t in c["context_list"]], mask_list=[t.to(dev) for t in c["mask_list"]],
+                y=None if c["y"] is None else c["y"].to(dev))
+
+
+def _engine(cfg, B, t5_len, **kw):
+    lens = (8, t5_len) if len([c for c in cfg["unet"]["context_dim"] if c is not None]) > 1 else (t5_len,)
+    return model.NativeLatentDiffusion(cfg, synth.unet_state_dict(cfg["unet"]), synth.vae_state_dict(cfg["vae"]),
+                                       synth.vocoder_state_dict(cfg["vocoder"]), B, DEV, ctx_max_len=lens, **kw)
+
+
+@pytest.fixture(scope="module")
+def tiny_tc():
+    return _engine(arch.tiny_config(), 2, 5, with_encoder=True)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_unet_tiny(impl, tiny_tc):
+    cfg = arch.tiny_config()
+    eng = tiny_tc if impl == "tc" else _engine(cfg, 2, 5, impl="simt", use_graph=False)
+    g = cases.load("unet_tiny")
+    x, t, cond, unc = cases.unet_inputs(cfg, 2, t5_len=5)
+    eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
+    assert torch.isfinite(e_c).all()
+    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL, impl
+    assert rel_l2(e_c, g["eps_cond"]) < NET_TOL, impl
+    # graph replay gives the same answer as the eager run
+    e_u2, e_c2 = eng.apply_model_pair(x.to(DEV), int(t[0]))
+    assert rel_l2(e_c2, g["eps_cond"]) < NET_TOL
+
+
+def test_unet_tiny_film():
+    cfg = arch.tiny_config(film=True)
+    eng = _engine(cfg, 2, 32)
+    g = cases.load("unet_tiny_film")
+    x, t, cond, unc = cases.unet_inputs(cfg, 2)
+    eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
+    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL and rel_l2(e_c, g["eps_cond"]) < NET_TOL
+
+
+def test_vae_and_vocoder_tiny(tiny_tc):
+    cfg = arch.tiny_config()
+    g = cases.load("vae_tiny")
+    mel = tiny_tc.decode_first_stage(cases.latent(cfg, 2, seed=5).to(DEV))
+    assert rel_l2(mel, g["mel"]) < NET_TOL
+    mom = tiny_tc.encode_first_stage_moments(cases.mel_input(cfg, 2).to(DEV))
+    assert rel_l2(mom.permute(0, 3, 1, 2), g["moments"]) < NET_TOL
+    gv = cases.load("vocoder_tiny")
+    # vocoder program is planned for the decoder's frame count; run the fixture through a dedicated plan
+    from audioldm2_b200 import engine, plan
+    pv = plan.build_vocoder(synth.vocoder_state_dict(cfg["vocoder"]), cfg["vocoder"], 24, 2)
+    prog = engine.DeviceProgram(pv, torch.device(DEV), dict(all=(0, len(pv.ops))))
+    prog.view("mel").copy_(cases.vocoder_input(cfg, 2, 24).permute(0, 2, 1).contiguous().to(DEV))
+    prog.run("all")
+    assert rel_l2(prog.view("wave"), gv["wave"]) < NET_TOL
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_ddim_tiny_vs_reference(masked, tiny_tc):
+    cfg = arch.tiny_config()
+    g = cases.load("ddim_tiny_masked" if masked else "ddim_tiny")
+    _, _, cond, unc = cases.unet_inputs(cfg, 2, t5_len=5)
+    x_T, noises, qn = cases.sampler_noise(cfg, 2, 5, masked=masked)
+    mask = x0 = None
+    if masked:
+        mask, x0 = cases.inpaint_mask(cfg, 2)
+        mask, x0 = mask.to(DEV), x0.to(DEV)
+    nf = lambda i, kind: (qn[i] if kind == "q" else noises[i]).to(DEV)
+    z = tiny_tc.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=5, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf,
+                                mask=mask, x0=x0)
+    assert rel_l2(z, g["latent"]) < 2e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size configuration (audioldm2-full), B = 1: the exact shapes of BASELINE config C1/C2
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full():
+    return _engine(arch.model_config("audioldm2-full"), 1, 32)
+
+
+def test_unet_full_vs_reference(full):
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load("unet_full")
+    x, t, cond, unc = cases.unet_inputs(cfg, 1)
+    full.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = full.apply_model_pair(x.to(DEV), int(t[0]))
+    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL
+    assert rel_l2(e_c, g["eps_cond"]) < NET_TOL
+
+
+def test_vae_vocoder_full_vs_reference(full):
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load("vae_full")
+    mel = full.decode_first_stage(cases.latent(cfg, 1, seed=5).to(DEV))
+    assert rel_l2(mel, g["mel"]) < NET_TOL
+    gv = cases.load("vocoder_full")
+    melin = cases.vocoder_input(cfg, 1, 1024).permute(0, 2, 1).contiguous()[:, None]      # [B,1,T,F]
+    w = full.mel_spectrogram_to_waveform(melin.to(DEV))
+    assert w.shape == (1, 1, 163872)
+    assert rel_l2(w, gv["wave"]) < NET_TOL
+
+
+@pytest.mark.parametrize("steps", [10, 200])
+def test_end_to_end_waveform_vs_reference(steps, full):
+    """x_T -> S x (2 UNet + update) -> VAE decode -> HiFi-GAN, identical noise; waveform within 1e-3."""
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load(f"ddim_full_{steps}")
+    _, _, cond, unc = cases.unet_inputs(cfg, 1)
+    x_T, noises, _ = cases.sampler_noise(cfg, 1, steps)
+    nf = lambda i, kind: noises[i].to(DEV)
+    z = full.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=steps, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf)
+    e_lat = rel_l2(z, g["latent"])
+    mel = full.decode_first_stage(z)
+    e_mel = rel_l2(mel, g["mel"])
+    wave = full.mel_spectrogram_to_waveform(mel)
+    e_wav = rel_l2(wave, g["wave"])
+    print(f"steps={steps}: latent {e_lat:.2e} mel {e_mel:.2e} waveform {e_wav:.2e}")
+    assert e_lat < WAVE_TOL and e_mel < WAVE_TOL and e_wav < WAVE_TOL
