@@ -78,10 +78,10 @@ def tiny_config(film: bool = False) -> dict:
     if film:
         unet.update(context_dim=[None], extra_film_condition_dim=24)
     vae = dict(ch=32, ch_mult=[1, 2, 4], num_res_blocks=1, z_channels=8, in_channels=1,
-               out_ch=1, embed_dim=8, double_z=True, mel_bins=16)
+               out_ch=1, embed_dim=8, double_z=True, mel_bins=32)
     voc = dict(upsample_rates=[5, 4, 2, 2, 2], upsample_kernel_sizes=[16, 16, 8, 4, 4],
                upsample_initial_channel=128, resblock_kernel_sizes=[3, 7, 11],
-               resblock_dilation_sizes=[[1, 3, 5]] * 3, num_mels=16,
+               resblock_dilation_sizes=[[1, 3, 5]] * 3, num_mels=32,
                n_fft=256, hop_size=40, win_size=256, sampling_rate=4000, fmin=0, fmax=2000)
     return dict(name="tiny-film" if film else "tiny", unet=unet, vae=vae, vocoder=voc,
                 latent=(8, 32, 8), sampling_rate=4000, latent_t_per_second=25.6,
