@@ -346,7 +346,12 @@ class Planner:
 
     def finish(self, io: Dict[str, object], meta=None) -> Plan:
         if self.splitk_ws_bytes:
-            ws = self.raw(self.splitk_ws_bytes)
+            # The split-K scratch is used by ops all along the program, so it must not come from the
+            # free list (those holes belong to buffers that are live at other points of the schedule):
+            # place it above the pool's high-water mark.
+            off = round_up(self.pool.peak, ALIGN)
+            self.pool.peak = off + round_up(self.splitk_ws_bytes, ALIGN)
+            ws = Ref("ws", off)
             for o in self.ops:
                 if o.get("ws") == "SPLITK":
                     o["ws"] = ws

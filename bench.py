@@ -26,6 +26,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+_CPU_THREADS = None
 METRIC = "10s clips/sec @200 DDIM steps (audioldm2-full)"
 UNIT = "clips/s"
 
@@ -43,6 +44,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write the per-op timing table of one UNet evaluation to this CSV")
+    ap.add_argument("--torch-cuda-baseline", action="store_true",
+                    help="also time the reference algorithm (oracle port, same torch ops as the reference modules) on the GPU")
     return ap.parse_args()
 
 
@@ -93,14 +97,33 @@ class ClockSampler:
 def cpu_sample(model_name: str, ddim_steps: int, t5_len: int, n_sample_steps: int = 1):
     from audioldm2_b200 import arch, synth
     from oracle import functional as OF
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cfg = arch.model_config(model_name)
     usd, vsd, hsd = synth.unet_state_dict(cfg["unet"]), synth.vae_state_dict(cfg["vae"]), synth.vocoder_state_dict(cfg["vocoder"])
     cond, unc = synth.conditioning(cfg, 1, seed=77, t5_len=t5_len)
     g = torch.Generator().manual_seed(0)
     C_, T, F_ = cfg["latent"]
     x = torch.randn(1, C_, T, F_, generator=g)
+    # use the thread count that is actually fastest on this host (all hardware threads is often NOT:
+    # torch's intra-op pool oversubscribes on small ops); the choice is reported in `cores`
+    global _CPU_THREADS
+    if _CPU_THREADS is None:
+        if "ALDM_CPU_THREADS" in os.environ:
+            _CPU_THREADS = int(os.environ["ALDM_CPU_THREADS"])
+        else:
+            n = os.cpu_count() or 1
+            best = None
+            for c in sorted({n, max(1, n // 2), max(1, n // 4), min(n, 16)}, reverse=True):
+                torch.set_num_threads(c)
+                ts = torch.full((1,), 501, dtype=torch.long)
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    OF.unet_forward(usd, cfg["unet"], x, ts, cond["context_list"], cond["mask_list"], cond["y"])
+                    dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, c)
+            _CPU_THREADS = best[1]
+    cores = _CPU_THREADS
+    torch.set_num_threads(cores)
     noises = [torch.randn(1, C_, T, F_, generator=g) for _ in range(n_sample_steps)]
     tables = OF.ddpm_tables(cfg["linear_start"], cfg["linear_end"], cfg["timesteps"])
     with torch.no_grad():
@@ -113,7 +136,7 @@ def cpu_sample(model_name: str, ddim_steps: int, t5_len: int, n_sample_steps: in
     per_step, dec = (t1 - t0) / n_sample_steps, t2 - t1
     clip_s = ddim_steps * per_step + dec
     sample = (f"B=1: {n_sample_steps} DDIM step(s) (2 UNet evals each, {per_step:.2f} s/step) + VAE decode + HiFi-GAN ({dec:.2f} s), "
-              f"fp32 torch CPU, {cores} threads; extrapolated to {ddim_steps} steps = {clip_s:.1f} s/clip")
+              f"fp32 torch CPU, {cores} threads (fastest of the tried counts; host has {os.cpu_count()}); extrapolated to {ddim_steps} steps = {clip_s:.1f} s/clip")
     return 1.0 / clip_s, cores, sample
 
 
@@ -139,7 +162,47 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------------
-def kernel_pass(eng, peaks: dict):
+def torch_cuda_baseline(model_name: str, B: int, ddim_steps: int, t5_len: int, dev, n_sample_steps: int = 3, tf32: bool = True):
+    """Reference PyTorch-CUDA baseline: the oracle port issues the same torch ops as the
+    reference modules (cuDNN conv, cuBLAS mm/bmm, ATen norms), two separate UNet calls per step as ddim.py:293-296."""
+    from audioldm2_b200 import arch, synth
+    from oracle import functional as OF
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32          # == set_float32_matmul_precision("high"), bin/audioldm2:139
+    cfg = arch.model_config(model_name)
+    mv = lambda sd: {k: v.to(dev) for k, v in sd.items()}
+    usd, vsd, hsd = mv(synth.unet_state_dict(cfg["unet"])), mv(synth.vae_state_dict(cfg["vae"])), mv(synth.vocoder_state_dict(cfg["vocoder"]))
+    cond, unc = synth.conditioning(cfg, B, seed=77, t5_len=t5_len, device=dev)
+    C_, T, F_ = cfg["latent"]
+    x = torch.randn(B, C_, T, F_, device=dev)
+    tables = OF.ddpm_tables(cfg["linear_start"], cfg["linear_end"], cfg["timesteps"])
+    sched = OF.ddim_schedule(tables, ddim_steps, 1.0)
+
+    def steps(n):
+        img = x
+        for st in sched[:n]:
+            ts = torch.full((B,), st["t"], dtype=torch.long, device=dev)
+            e_u = OF.unet_forward(usd, cfg["unet"], img, ts, unc["context_list"], unc["mask_list"], unc["y"])
+            e_c = OF.unet_forward(usd, cfg["unet"], img, ts, cond["context_list"], cond["mask_list"], cond["y"])
+            img, _ = OF.ddim_update(img, e_u, e_c, torch.randn_like(img), st, 3.5)
+        return img
+
+    def dec(z):
+        mel = OF.vae_decode(vsd, cfg["vae"], z)
+        return OF.vocoder_forward(hsd, cfg["vocoder"], mel.squeeze(1).permute(0, 2, 1)).cpu()
+
+    with torch.no_grad():
+        z = steps(1); dec(z); torch.cuda.synchronize()          # warm-up (cuDNN autotune, allocator)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(); z = steps(n_sample_steps); e[1].record(); dec(z); e[2].record(); torch.cuda.synchronize()
+    per_step, tdec = e[0].elapsed_time(e[1]) * 1e-3 / n_sample_steps, e[1].elapsed_time(e[2]) * 1e-3
+    total = ddim_steps * per_step + tdec
+    return dict(value=B / total, unit=UNIT, tf32=tf32,
+                sample=f"B={B}: {n_sample_steps} DDIM steps ({per_step * 1e3:.1f} ms/step, 2 UNet calls each) + decode+vocode ({tdec * 1e3:.0f} ms); "
+                       f"extrapolated to {ddim_steps} steps = {total:.2f} s/batch")
+
+
+def kernel_pass(eng, peaks: dict, dump=None):
     """Per-launch CUDA-event timing of ONE UNet evaluation (eager, same stream), aggregated for the
     dominant kernel = gemm_tc_kernel: achieved = sum(algorithmic FLOPs) / sum(durations)."""
     from audioldm2_b200 import _lib
@@ -166,6 +229,21 @@ def kernel_pass(eng, peaks: dict):
             fl += 2.0 * M * o["N"] * o["K"]
             tm += ms
     total = sum(per_kind.values())
+    if dump:
+        with open(dump, "w") as f:
+            f.write("idx,kind,tag,ms,M,N,K,taps,splitk,bn,tflops\n")
+            for i in range(n):
+                o = pl.ops[a + i]
+                ms = evs[i].elapsed_time(evs[i + 1])
+                if o["kind"] == "gemm":
+                    M = o["B"] * o["OH"] * o["OW"]
+                    f.write(f"{i},gemm,{o['tag']},{ms:.4f},{M},{o['N']},{o['K']},{o['ntaps']},{o['splitk']},{o['bn']},"
+                            f"{2.0 * M * o['N'] * o['K'] / (ms * 1e-3) / 1e12:.1f}\n")
+                elif o["kind"] == "attn":
+                    f.write(f"{i},attn,{o['tag']},{ms:.4f},{o['B'] * o['Nq']},{o['Nk']},{o['heads']},0,0,0,"
+                            f"{4.0 * o['B'] * o['heads'] * o['Nq'] * o['Nk'] * 32 / (ms * 1e-3) / 1e12:.1f}\n")
+                else:
+                    f.write(f"{i},{o['kind']},{o.get('tag', 0)},{ms:.4f},{o.get('rows', 0)},{o.get('c0', 0)},0,0,0,0,0\n")
     peak = peaks.get("bf16_tflops_sustained") or 1432.6
     ach = fl / (tm * 1e-3) / 1e12 if tm > 0 else 0.0
     return dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
@@ -241,7 +319,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roof = None if a.no_kernel_pass else kernel_pass(eng, peaks)
+    roof = None if a.no_kernel_pass else kernel_pass(eng, peaks, a.dump_ops)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if roof is not None:
@@ -252,6 +330,12 @@ def main():
     if world == 1 and not a.no_cpu_baseline:
         v, cores, sample = cpu_sample(a.model, S, a.t5_len, 1)
         cpu = dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample)
+    tcb = None
+    if a.torch_cuda_baseline and world == 1:
+        del eng
+        torch.cuda.empty_cache()
+        tcb = dict(tf32=torch_cuda_baseline(a.model, B, S, a.t5_len, dev, tf32=True),
+                   fp32=torch_cuda_baseline(a.model, B, S, a.t5_len, dev, tf32=False))
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=1000.0 * t_dev / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="bf16x3 (fp32-faithful split-bf16 tensor-core operands, fp32 accumulate)", data="synthetic",
@@ -261,6 +345,8 @@ def main():
                             parallelism=f"dp{world} (independent batch shards, weights broadcast once over NCCL)"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=wave_host.numel() * 4),
                 gpu_launches=launches, clocks=clk, roofline=roof, cpu_baseline=cpu, impl="native")
+    if tcb is not None:
+        line["torch_cuda_baseline"] = tcb
     print(json.dumps(line))
 
 

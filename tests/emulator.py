@@ -145,6 +145,11 @@ class Emulator:
 
     def op_gemm(self, o):
         B, H, W, Cp, up = o["B"], o["H"], o["W"], o["Cp"], o["up"]
+        if o["splitk"] > 1:
+            # the kernel scribbles partial sums over its split-K workspace: emulate the clobber so an
+            # overlap with a live buffer is caught
+            n = o["splitk"] * packing.round_up(B * o["OH"] * o["OW"], 128) * packing.round_up(o["N"], o["bn"])
+            self.f32(o["ws"], n)[:] = float("nan")
         OH, OW, sy, sx = o["OH"], o["OW"], o["sy"], o["sx"]
         Hs, Ws = H >> up, W >> up
         bmod = o["bmod"]

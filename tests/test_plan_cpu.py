@@ -60,7 +60,8 @@ def _run_unet(cfg, B, t5_len, fixture, film=False):
     sd = synth.unet_state_dict(cfg["unet"])
     x, t, cond, unc = cases.unet_inputs(cfg, B, t5_len=t5_len)
     lens = tuple(c.shape[1] for c in cond["context_list"]) or (8,)
-    pl = plan.build_unet(sd, cfg["unet"], cfg["latent"], B, ctx_max_len=lens, keep_plain=True)
+    pl = plan.build_unet(sd, cfg["unet"], cfg["latent"], B, ctx_max_len=lens, keep_plain=True)   # impl=tc: split-K on
+    assert any(o["kind"] == "gemm" and o["splitk"] > 1 for o in pl.ops)
     em = Emulator(pl)
     em.write_io("x", x)
     em.write_io("t", torch.cat([t, t]))
