@@ -20,12 +20,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
 MAX_TAPS = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums (keep in sync with the header; checked by tests/test_abi.py against the header text)
 GEMM_TC, GEMM_SIMT = 0, 1
 ACT_NONE, ACT_GEGLU, ACT_TANH, ACT_SILU = 0, 1, 2, 3
-OUT_F32, OUT_PLANES, OUT_NCHW = 0, 1, 2
+OUT_F32, OUT_PLANES, OUT_NCHW, OUT_QKV = 0, 1, 2, 3
 PREP_COPY, PREP_SILU, PREP_LRELU, PREP_GN, PREP_GN_SILU, PREP_LN = 0, 1, 2, 3, 4, 5
 OP_GEMM, OP_PREP, OP_ATTN, OP_SOFTMAX, OP_TEMB, OP_TRANSPOSE, OP_PACKB, OP_COPY = 1, 2, 3, 4, 5, 6, 7, 8
 
@@ -34,7 +34,8 @@ class GemmDesc(C.Structure):
     _fields_ = [
         ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("w_packed", C.c_void_p), ("w_plain", C.c_void_p),
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p),
-        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ws", C.c_void_p),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out2_hi", C.c_void_p), ("out2_lo", C.c_void_p),
+        ("ws", C.c_void_p),
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cp", C.c_int32),
         ("up", C.c_int32), ("bmod", C.c_int32),
         ("OH", C.c_int32), ("OW", C.c_int32), ("sy", C.c_int32), ("sx", C.c_int32),
@@ -44,7 +45,8 @@ class GemmDesc(C.Structure):
         ("ldo", C.c_int32), ("ld_res", C.c_int32), ("ld_rowvec", C.c_int32),
         ("OHF", C.c_int32), ("OWF", C.c_int32), ("osy", C.c_int32), ("ooy", C.c_int32),
         ("act", C.c_int32), ("out_mode", C.c_int32), ("accumulate", C.c_int32), ("splitk", C.c_int32),
-        ("impl", C.c_int32), ("alpha", C.c_float),
+        ("impl", C.c_int32), ("n_split", C.c_int32), ("tok_per_batch", C.c_int32), ("ld_t", C.c_int32),
+        ("alpha", C.c_float),
     ]
 
 
@@ -60,11 +62,13 @@ class PrepDesc(C.Structure):
 
 class AttnDesc(C.Structure):
     _fields_ = [
-        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("mask", C.c_void_p),
+        ("q_hi", C.c_void_p), ("q_lo", C.c_void_p), ("k_hi", C.c_void_p), ("k_lo", C.c_void_p),
+        ("vt_hi", C.c_void_p), ("vt_lo", C.c_void_p), ("mask", C.c_void_p),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
         ("B", C.c_int32), ("heads", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32),
-        ("ldq", C.c_int32), ("ldk", C.c_int32), ("ldv", C.c_int32), ("ldo", C.c_int32),
-        ("kv_bmod", C.c_int32), ("scale", C.c_float),
+        ("ldq", C.c_int32), ("ldk", C.c_int32), ("ld_t", C.c_int32), ("ldo", C.c_int32),
+        ("q_col", C.c_int32), ("k_col", C.c_int32), ("kv_bmod", C.c_int32), ("impl", C.c_int32),
+        ("scale", C.c_float),
     ]
 
 

@@ -1,10 +1,21 @@
-// K5 (first version): fused softmax(scale * Q K^T + mask) V, head_dim 32, flash-style online softmax.
-// One thread owns one query row (q and the output accumulator live in registers); K/V tiles of
-// 64 keys are staged in shared memory and broadcast-read.  No N x N score matrix touches HBM
-// (the reference materialises it: attention.py:354-366).  fp32 FMA on CUDA cores -- exact w.r.t.
-// the oracle; the tcgen05 version replaces the two inner products.
+// K5: fused softmax(scale * Q K^T + mask) V, head_dim 32, flash-style (no N x N score matrix in HBM;
+// the reference materialises it: attention.py:354-366).
 //
-// Also: row softmax for the VAE AttnBlock (model.py:216-217) whose scores come from the GEMM.
+// attention_tc_kernel (tcgen05): one CTA = 128 queries of one (batch, head); keys are streamed in
+// tiles of 64.  Operands are the bf16 hi/lo planes written by the projection GEMMs
+// (ALDM_OUT_QKV): Q, K row-major, V already transposed (keys contiguous), so every operand tile is
+// a plain cp.async copy into the same 128-byte-swizzled K-major layout the GEMM uses.
+//   S = Q K^T       : [q_hi|q_hi] x [k_hi|k_lo]^T (K=64) + [q_lo] x [k_hi]^T (K=32)   -> TMEM (6 UMMAs)
+//   softmax          : 128 threads, one query row each (TMEM lane == row), online max/sum in the
+//                      log2 domain, P split to bf16 hi/lo and written to shared memory as the A operand
+//   O_tile = P V     : 3 passes x 4 K-steps, N = 32                                    -> TMEM (12 UMMAs)
+//   O += rescaled O_tile in registers (no TMEM read-modify-write)
+// Warp roles: 0-3 softmax/epilogue, 4 loader (cp.async + mbarrier), 5 TMEM alloc + MMA issue.
+// ~97 KB shared memory and 128 TMEM columns per CTA -> two CTAs per SM overlap each other's MMA
+// and softmax phases.
+//
+// attention_simt_kernel: CUDA-core checker on the same operands (validation only).
+// softmax_rows_kernel: row softmax for the VAE AttnBlock (model.py:216-217).
 #include <float.h>
 
 #include "common.cuh"
@@ -12,114 +23,268 @@
 namespace aldm {
 
 static constexpr int ATT_D = 32;
-static constexpr int ATT_KT = 64;   // keys per shared-memory tile
 
-__global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ aldm_attn_desc d) {
-  __shared__ __align__(16) float sK[ATT_KT][ATT_D];
-  __shared__ __align__(16) float sV[ATT_KT][ATT_D];
-  __shared__ float sM[ATT_KT];
+// ------------------------------------------------------------------------------------------------
+// tcgen05 flash attention
+// ------------------------------------------------------------------------------------------------
+namespace atc {
+constexpr int QT = 128, KT = 64;
+constexpr int QA1 = 0;                         // [128][128B]  q_hi | q_hi
+constexpr int QA2 = QA1 + QT * 128;            // [128][128B]  q_lo | -
+constexpr int KB = QA2 + QT * 128;             // 2 x [64][128B]   k_hi | k_lo
+constexpr int VT = KB + 2 * KT * 128;          // 2 x {hi,lo} x [32][128B]
+constexpr int PP = VT + 2 * 2 * ATT_D * 128;   // {hi,lo} x [128][128B]
+constexpr int BAR = PP + 2 * QT * 128;
+constexpr int SMEM = BAR + 128 + 1024;
+constexpr int TMEM_COLS = 128;                 // S: cols [0,64), O_tile: cols [64,96)
+}  // namespace atc
+
+__global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_constant__ aldm_attn_desc d) {
+  using namespace atc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar = base + BAR;
+  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 24, s_full = bar + 40, p_full = bar + 48,
+                 o_full = bar + 56, tmem_slot = bar + 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
+  const int nt = (d.Nk + KT - 1) / KT;
+
+  if (tid == 0) {
+    mbar_init(q_full, 32);
+    mbar_init(kv_full0, 32); mbar_init(kv_full0 + 8, 32);
+    mbar_init(kv_empty0, 1); mbar_init(kv_empty0 + 8, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + BAR + 64);
+  const uint32_t tmem_S = tmem, tmem_O = tmem + 64;
+
+  if (warp < 4) {
+    // =============================== softmax + output ===============================
+    const int row = tid, q = q0 + row;
+    const float sl2 = d.scale * 1.4426950408889634f;
+    const uint32_t trow = (uint32_t)(warp * 32) << 16;
+    const uint32_t swz = (uint32_t)(row & 7);
+    float o[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+    float mrun = -INFINITY, lrun = 0.f;
+    const float* mrow = d.mask ? d.mask + (long long)bkv * d.Nk : nullptr;
+    for (int it = 0; it < nt; ++it) {
+      const int k0 = it * KT;
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float s[KT];
+      tmem_ld32(tmem_S + trow, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(tmem_S + trow + 32, reinterpret_cast<uint32_t*>(s + 32));
+      tmem_ld_wait();
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        const int key = k0 + j;
+        float v = s[j] * sl2;
+        if (key >= d.Nk) v = -INFINITY;                               // beyond the key range: excluded
+        else if (mrow && __ldg(mrow + key) != 1.0f) v = -FLT_MAX;     // masked_fill(-finfo.max), attention.py:356-360
+        s[j] = v;
+        tmax = fmaxf(tmax, v);
+      }
+      const float mnew = fmaxf(mrun, tmax);
+      const float corr = (mrun == -INFINITY) ? 0.f : exp2f(mrun - mnew);
+      float psum = 0.f;
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        const float p = (s[j] == -INFINITY) ? 0.f : exp2f(s[j] - mnew);
+        s[j] = p;
+        psum += p;
+      }
+      lrun = lrun * corr + psum;
+      mrun = mnew;
+      uint8_t* ph = sm + PP + row * 128;
+#pragma unroll
+      for (int c = 0; c < KT / 8; ++c) {
+        uint4 hi, lo;
+        split8(s + c * 8, hi, lo);
+        const uint32_t off = ((uint32_t)c ^ swz) << 4;
+        *reinterpret_cast<uint4*>(ph + off) = hi;
+        *reinterpret_cast<uint4*>(ph + QT * 128 + off) = lo;
+      }
+      fence_proxy_async();          // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      float ot[ATT_D];
+      tmem_ld32(tmem_O + trow, reinterpret_cast<uint32_t*>(ot));
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < ATT_D; ++i) o[i] = fmaf(o[i], corr, ot[i]);
+    }
+    tc_fence_before();
+    if (q < d.Nq) {
+      const float inv = 1.0f / lrun;
+#pragma unroll
+      for (int i = 0; i < ATT_D; ++i) o[i] *= inv;
+      const long long orow = (long long)b * d.Nq + q;
+      __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + h * ATT_D;
+      __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + h * ATT_D;
+#pragma unroll
+      for (int i = 0; i < ATT_D; i += 8) {
+        uint4 hh, ll;
+        split8(o + i, hh, ll);
+        *reinterpret_cast<uint4*>(hp + i) = hh;
+        *reinterpret_cast<uint4*>(lp + i) = ll;
+      }
+    }
+  } else if (warp == 4) {
+    // =============================== loader ===============================
+    const __nv_bfloat16* qh = reinterpret_cast<const __nv_bfloat16*>(d.q_hi);
+    const __nv_bfloat16* ql = reinterpret_cast<const __nv_bfloat16*>(d.q_lo);
+    const __nv_bfloat16* kh = reinterpret_cast<const __nv_bfloat16*>(d.k_hi);
+    const __nv_bfloat16* kl = reinterpret_cast<const __nv_bfloat16*>(d.k_lo);
+    const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(d.vt_hi);
+    const __nv_bfloat16* vl = reinterpret_cast<const __nv_bfloat16*>(d.vt_lo);
+    // Q: QA1 row r chunk c <- q_hi chunk (c & 3); QA2 row r chunk c (c < 4) <- q_lo chunk c
+    for (int idx = lane; idx < QT * 8; idx += 32) {
+      const int r = idx >> 3, c = idx & 7;
+      const bool ok = q0 + r < d.Nq;
+      const long long off = ok ? ((long long)b * d.Nq + q0 + r) * d.ldq + d.q_col + h * ATT_D + (c & 3) * 8 : 0;
+      const uint32_t dst = base + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4);
+      cp_async_16(dst + QA1, qh + off, ok ? 16u : 0u);
+      if (c < 4) cp_async_16(dst + QA2, ql + off, ok ? 16u : 0u);
+    }
+    cp_async_mbar_arrive_noinc(q_full);
+    for (int it = 0; it < nt; ++it) {
+      const int s = it & 1, k0 = it * KT;
+      mbar_wait(kv_empty0 + 8 * s, ((it >> 1) & 1) ^ 1);
+      const uint32_t kb = base + KB + s * (KT * 128);
+      for (int idx = lane; idx < KT * 8; idx += 32) {
+        const int r = idx >> 3, c = idx & 7;
+        const bool ok = k0 + r < d.Nk;
+        const long long off = ok ? ((long long)bkv * d.Nk + k0 + r) * d.ldk + d.k_col + h * ATT_D + (c & 3) * 8 : 0;
+        cp_async_16(kb + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), (c < 4 ? kh : kl) + off, ok ? 16u : 0u);
+      }
+      const uint32_t vb = base + VT + s * (2 * ATT_D * 128);
+      for (int idx = lane; idx < 2 * ATT_D * 8; idx += 32) {
+        const int p = idx >> 8, r = (idx >> 3) & 31, c = idx & 7;        // plane, d row, 8-key chunk
+        const bool ok = k0 + c * 8 < d.Nk;
+        const long long off = ok ? ((long long)(bkv * d.heads + h) * ATT_D + r) * d.ld_t + k0 + c * 8 : 0;
+        cp_async_16(vb + p * (ATT_D * 128) + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), (p ? vl : vh) + off, ok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive_noinc(kv_full0 + 8 * s);
+    }
+  } else {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idS = umma_idesc_bf16(128, KT), idO = umma_idesc_bf16(128, ATT_D);
+      const uint64_t dA1 = umma_desc_sw128(base + QA1), dA2 = umma_desc_sw128(base + QA2);
+      const uint64_t dPh = umma_desc_sw128(base + PP), dPl = umma_desc_sw128(base + PP + QT * 128);
+      mbar_wait(q_full, 0);
+      for (int it = 0; it < nt; ++it) {
+        const int s = it & 1;
+        mbar_wait(kv_full0 + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+        fence_proxy_async();
+        const uint64_t dK = umma_desc_sw128(base + KB + s * (KT * 128));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_S, dA1 + 2 * ks, dK + 2 * ks, idS, ks > 0);   // q_hi k_hi + q_hi k_lo
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem_S, dA2 + 2 * ks, dK + 2 * ks, idS, 1);        // q_lo k_hi
+        umma_commit(s_full);
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+        fence_proxy_async();
+        const uint64_t dVh = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128));
+        const uint64_t dVl = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128) + ATT_D * 128);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_bf16(tmem_O, dPl + 2 * ks, dVh + 2 * ks, idO, ks > 0);
+          umma_bf16(tmem_O, dPh + 2 * ks, dVl + 2 * ks, idO, 1);
+          umma_bf16(tmem_O, dPh + 2 * ks, dVh + 2 * ks, idO, 1);
+        }
+        umma_commit(o_full);
+        umma_commit(kv_empty0 + 8 * s);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core checker on the same plane operands: one thread per query, fp32
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attention_simt_kernel(const __grid_constant__ aldm_attn_desc d) {
   const int b = blockIdx.z, h = blockIdx.y;
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool qvalid = qi < d.Nq;
+  if (qi >= d.Nq) return;
   const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
+  auto ld = [](const void* hi, const void* lo, long long i) {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(hi)[i]) +
+           __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(lo)[i]);
+  };
   float q[ATT_D], o[ATT_D];
-  {
-    const float* qp = d.q + ((long long)b * d.Nq + (qvalid ? qi : 0)) * d.ldq + h * ATT_D;
-#pragma unroll
-    for (int i = 0; i < ATT_D; i += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(qp + i);
-      q[i] = t.x * d.scale; q[i + 1] = t.y * d.scale; q[i + 2] = t.z * d.scale; q[i + 3] = t.w * d.scale;
-    }
+  for (int i = 0; i < ATT_D; ++i) {
+    q[i] = ld(d.q_hi, d.q_lo, ((long long)b * d.Nq + qi) * d.ldq + d.q_col + h * ATT_D + i) * d.scale;
+    o[i] = 0.f;
   }
-#pragma unroll
-  for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
   float mrun = -INFINITY, lrun = 0.f;
-
-  for (int k0 = 0; k0 < d.Nk; k0 += ATT_KT) {
-    const int kn = min(ATT_KT, d.Nk - k0);
-    __syncthreads();
-    // cooperative load: 64 keys x 32 floats = 512 float4 for K and for V
-    for (int idx = threadIdx.x; idx < ATT_KT * (ATT_D / 4); idx += blockDim.x) {
-      const int kk = idx / (ATT_D / 4), c4 = (idx % (ATT_D / 4)) * 4;
-      float4 tk = make_float4(0.f, 0.f, 0.f, 0.f), tv = tk;
-      if (kk < kn) {
-        const long long rowk = (long long)bkv * d.Nk + k0 + kk;
-        tk = *reinterpret_cast<const float4*>(d.k + rowk * d.ldk + h * ATT_D + c4);
-        tv = *reinterpret_cast<const float4*>(d.v + rowk * d.ldv + h * ATT_D + c4);
-      }
-      *reinterpret_cast<float4*>(&sK[kk][c4]) = tk;
-      *reinterpret_cast<float4*>(&sV[kk][c4]) = tv;
-    }
-    for (int kk = threadIdx.x; kk < ATT_KT; kk += blockDim.x)
-      sM[kk] = (d.mask && kk < kn) ? d.mask[(long long)bkv * d.Nk + k0 + kk] : 1.0f;
-    __syncthreads();
-
-    for (int c0 = 0; c0 < kn; c0 += 8) {
-      float s[8];
-      float cmax = -INFINITY;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int kk = c0 + jj;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < ATT_D; i += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(&sK[kk < kn ? kk : 0][i]);
-          acc = fmaf(q[i], t.x, acc); acc = fmaf(q[i + 1], t.y, acc);
-          acc = fmaf(q[i + 2], t.z, acc); acc = fmaf(q[i + 3], t.w, acc);
-        }
-        if (kk >= kn) acc = -INFINITY;                     // beyond the key range: excluded
-        else if (sM[kk] != 1.0f) acc = -FLT_MAX;           // masked_fill(-finfo.max), attention.py:356-360
-        s[jj] = acc;
-        cmax = fmaxf(cmax, acc);
-      }
-      const float mnew = fmaxf(mrun, cmax);
-      const float corr = (mrun == -INFINITY) ? 0.f : expf(mrun - mnew);
-      lrun *= corr;
-#pragma unroll
-      for (int i = 0; i < ATT_D; ++i) o[i] *= corr;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int kk = c0 + jj;
-        const float p = (s[jj] == -INFINITY) ? 0.f : expf(s[jj] - mnew);
-        lrun += p;
-#pragma unroll
-        for (int i = 0; i < ATT_D; i += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(&sV[kk < kn ? kk : 0][i]);
-          o[i] = fmaf(p, t.x, o[i]); o[i + 1] = fmaf(p, t.y, o[i + 1]);
-          o[i + 2] = fmaf(p, t.z, o[i + 2]); o[i + 3] = fmaf(p, t.w, o[i + 3]);
-        }
-      }
-      mrun = mnew;
-    }
+  for (int k = 0; k < d.Nk; ++k) {
+    float s = 0.f;
+    const long long kr = ((long long)bkv * d.Nk + k) * d.ldk + d.k_col + h * ATT_D;
+    for (int i = 0; i < ATT_D; ++i) s = fmaf(q[i], ld(d.k_hi, d.k_lo, kr + i), s);
+    if (d.mask && d.mask[(long long)bkv * d.Nk + k] != 1.0f) s = -FLT_MAX;
+    const float mnew = fmaxf(mrun, s);
+    const float corr = (mrun == -INFINITY) ? 0.f : expf(mrun - mnew);
+    const float p = expf(s - mnew);
+    lrun = lrun * corr + p;
+    for (int i = 0; i < ATT_D; ++i)
+      o[i] = o[i] * corr + p * ld(d.vt_hi, d.vt_lo, ((long long)(bkv * d.heads + h) * ATT_D + i) * d.ld_t + k);
+    mrun = mnew;
   }
-  if (!qvalid) return;
-  const float inv = 1.0f / lrun;
-#pragma unroll
-  for (int i = 0; i < ATT_D; ++i) o[i] *= inv;
   const long long orow = (long long)b * d.Nq + qi;
   __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + h * ATT_D;
   __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + h * ATT_D;
-#pragma unroll
-  for (int i = 0; i < ATT_D; i += 8) {
-    uint4 hh, ll;
-    split8(o + i, hh, ll);
-    *reinterpret_cast<uint4*>(hp + i) = hh;
-    *reinterpret_cast<uint4*>(lp + i) = ll;
+  for (int i = 0; i < ATT_D; ++i) {
+    const float v = o[i] / lrun;
+    const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+    hp[i] = hh;
+    lp[i] = __float2bfloat16_rn(v - __bfloat162float(hh));
   }
 }
 
 int attention_launch(const aldm_attn_desc& d, cudaStream_t st) {
-  ALDM_REQUIRE(d.q && d.k && d.v && d.out_hi && d.out_lo, ALDM_E_ARG, "attention: null pointer");
+  ALDM_REQUIRE(d.q_hi && d.q_lo && d.k_hi && d.k_lo && d.vt_hi && d.vt_lo && d.out_hi && d.out_lo, ALDM_E_ARG,
+               "attention: null pointer");
   ALDM_REQUIRE(d.B > 0 && d.heads > 0 && d.Nq > 0 && d.Nk > 0, ALDM_E_SHAPE, "attention: B=%d heads=%d Nq=%d Nk=%d", d.B,
                d.heads, d.Nq, d.Nk);
-  ALDM_REQUIRE(d.ldq % 4 == 0 && d.ldk % 4 == 0 && d.ldv % 4 == 0 && d.ldo % 8 == 0, ALDM_E_ALIGN,
-               "attention: leading dims must be multiples of 4 (ldo of 8)");
-  ALDM_REQUIRE(aligned16(d.q) && aligned16(d.k) && aligned16(d.v) && aligned16(d.out_hi) && aligned16(d.out_lo),
+  ALDM_REQUIRE(d.ldq % 8 == 0 && d.ldk % 8 == 0 && d.ld_t % 8 == 0 && d.ldo % 8 == 0 && d.q_col % 8 == 0 && d.k_col % 8 == 0,
+               ALDM_E_ALIGN, "attention: leading dims / column offsets must be multiples of 8");
+  ALDM_REQUIRE(d.ld_t >= d.Nk, ALDM_E_SHAPE, "attention: ld_t=%d < Nk=%d", d.ld_t, d.Nk);
+  ALDM_REQUIRE(aligned16(d.q_hi) && aligned16(d.q_lo) && aligned16(d.k_hi) && aligned16(d.k_lo) && aligned16(d.vt_hi) &&
+                   aligned16(d.vt_lo) && aligned16(d.out_hi) && aligned16(d.out_lo),
                ALDM_E_ALIGN, "attention: pointers must be 16B aligned");
   ALDM_REQUIRE(d.heads <= 65535 && d.B <= 65535, ALDM_E_SHAPE, "attention: grid too large");
-  const int threads = d.Nq >= 128 ? 128 : ((d.Nq + 31) / 32) * 32;
-  dim3 grid(cdiv(d.Nq, threads), d.heads, d.B);
-  attention_kernel<<<grid, threads, 0, st>>>(d);
+  if (d.impl == ALDM_GEMM_SIMT) {
+    dim3 grid(cdiv(d.Nq, 128), d.heads, d.B);
+    attention_simt_kernel<<<grid, 128, 0, st>>>(d);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM));
+      configured = true;
+    }
+    dim3 grid(cdiv(d.Nq, atc::QT), d.heads, d.B);
+    attention_tc_kernel<<<grid, 192, atc::SMEM, st>>>(d);
+  }
   ALDM_CHECK_CUDA(cudaGetLastError());
   return ALDM_OK;
 }

@@ -24,13 +24,14 @@ namespace aldm {
 // row decoding + epilogue shared by the tensor-core kernel, the SIMT checker and split-K
 // ------------------------------------------------------------------------------------------
 struct RowInfo {
-  int b, oh, ow;
+  int m, b, oh, ow;
   bool valid;
   long long orow;
 };
 
 __device__ __forceinline__ RowInfo decode_row(const aldm_gemm_desc& d, int m, int M) {
   RowInfo r;
+  r.m = m;
   r.valid = m < M;
   int mm = r.valid ? m : 0;
   r.ow = mm % d.OW;
@@ -63,7 +64,27 @@ __device__ __forceinline__ void epi_finish(const aldm_gemm_desc& d, const RowInf
     } else {
       for (int i = 0; i < cnt; ++i) op[i] = v[i];
     }
-  } else if (d.out_mode == ALDM_OUT_PLANES) {
+  } else if (d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split) {
+    // V projection: transposed planes [(b*Cv + c), ld_t] with the token index contiguous
+    const int b = r.m / d.tok_per_batch, tok = r.m - b * d.tok_per_batch;
+    const long long base = ((long long)b * (d.N - d.n_split) + (n0 - d.n_split)) * d.ld_t + tok;
+    __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out2_hi) + base;
+    __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out2_lo) + base;
+    for (int i = 0; i < cnt; ++i) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+      hp[(long long)i * d.ld_t] = h;
+      lp[(long long)i * d.ld_t] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+    }
+    // keys in [tok_per_batch, ld_t) are padding the attention kernel multiplies by P = 0: they must
+    // be finite (stale workspace bytes reinterpreted as bf16 could be NaN), so the last token zeroes them
+    if (tok == d.tok_per_batch - 1) {
+      for (int t = 1; tok + t < d.ld_t; ++t)
+        for (int i = 0; i < cnt; ++i) {
+          hp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
+          lp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
+        }
+    }
+  } else if (d.out_mode == ALDM_OUT_PLANES || d.out_mode == ALDM_OUT_QKV) {
     __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + r.orow * d.ldo + n0;
     __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + r.orow * d.ldo + n0;
     if (cnt == 32 && ((reinterpret_cast<uintptr_t>(hp) & 15u) == 0)) {
@@ -450,6 +471,12 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
   if (d.act == ALDM_ACT_GEGLU) {
     ALDM_REQUIRE(d.bn >= 64 && d.N % d.bn == 0, ALDM_E_SHAPE, "gemm: GEGLU needs N %% bn == 0 and bn >= 64");
     ALDM_REQUIRE(!d.rowvec, ALDM_E_UNSUPPORTED, "gemm: GEGLU with rowvec");
+  }
+  if (d.out_mode == ALDM_OUT_QKV) {
+    ALDM_REQUIRE(d.out2_hi && d.out2_lo && d.n_split > 0 && d.n_split < d.N && d.n_split % d.bn == 0 && d.n_split % 32 == 0,
+                 ALDM_E_ARG, "gemm: bad QKV split (n_split=%d, N=%d, bn=%d)", d.n_split, d.N, d.bn);
+    ALDM_REQUIRE(d.tok_per_batch > 0 && d.ld_t >= d.tok_per_batch && d.act != ALDM_ACT_GEGLU, ALDM_E_ARG,
+                 "gemm: bad QKV token layout");
   }
   if (d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_NCHW) {
     ALDM_REQUIRE(d.out, ALDM_E_ARG, "gemm: null out");

@@ -146,6 +146,7 @@ extern "C" size_t aldm_offsetof_gemm(int32_t field) {
     case 4: return offsetof(aldm_gemm_desc, ldo);
     case 5: return offsetof(aldm_gemm_desc, act);
     case 6: return offsetof(aldm_gemm_desc, alpha);
+    case 7: return offsetof(aldm_gemm_desc, n_split);
     default: return (size_t)-1;
   }
 }

@@ -61,6 +61,13 @@ class Planes:         # bf16 hi/lo operand planes [rows, Cp]
 
 
 @dataclass
+class VT:             # transposed V planes [(b*C + c), ld_t] (keys contiguous), written by an ALDM_OUT_QKV GEMM
+    hi: Ref
+    lo: Ref
+    ld_t: int
+
+
+@dataclass
 class WMat:           # packed weight matrix
     packed: Ref
     plain: Optional[Ref]
@@ -164,8 +171,11 @@ class Plan:
             if k == "gemm":
                 op.kind = _lib.OP_GEMM
                 g = op.u.gemm
-                for name in ("a_hi", "a_lo", "w_packed", "w_plain", "bias", "rowvec", "res", "out", "out_hi", "out_lo", "ws"):
+                for name in ("a_hi", "a_lo", "w_packed", "w_plain", "bias", "rowvec", "res", "out", "out_hi", "out_lo",
+                             "out2_hi", "out2_lo", "ws"):
                     setattr(g, name, P(o.get(name)))
+                for name in ("n_split", "tok_per_batch", "ld_t"):
+                    setattr(g, name, int(o.get(name, 0)))
                 for name in ("B", "H", "W", "Cp", "up", "bmod", "OH", "OW", "sy", "sx", "ntaps", "N", "K", "Kpad", "bn",
                              "ldo", "ld_res", "ld_rowvec", "OHF", "OWF", "osy", "ooy", "act", "out_mode", "accumulate",
                              "splitk", "impl"):
@@ -185,9 +195,9 @@ class Plan:
             elif k == "attn":
                 op.kind = _lib.OP_ATTN
                 a = op.u.attn
-                for name in ("q", "k", "v", "mask", "out_hi", "out_lo"):
+                for name in ("q_hi", "q_lo", "k_hi", "k_lo", "vt_hi", "vt_lo", "mask", "out_hi", "out_lo"):
                     setattr(a, name, P(o.get(name)))
-                for name in ("B", "heads", "Nq", "Nk", "ldq", "ldk", "ldv", "ldo", "kv_bmod"):
+                for name in ("B", "heads", "Nq", "Nk", "ldq", "ldk", "ld_t", "ldo", "q_col", "k_col", "kv_bmod", "impl"):
                     setattr(a, name, int(o[name]))
                 a.scale = float(o["scale"])
             elif k == "softmax":
@@ -253,6 +263,13 @@ class Planner:
         return WMat(Ref("w", self.arena.add(packed)), Ref("w", self.arena.add(plain)) if self.keep_plain else None,
                     bref, N, K, Kpad, bn, cp, ntaps)
 
+    @staticmethod
+    def bn_for_split(N: int, n_split: int) -> int:
+        for b in (128, 64, 32):
+            if n_split % b == 0 and N % b == 0:
+                return b
+        raise ValueError((N, n_split))
+
     def conv_w(self, sd, name: str, scale: float = 1.0) -> WMat:
         w = sd[name + ".weight"].float() * scale
         wm, taps, cp = packing.conv_weight_matrix(w)
@@ -270,11 +287,23 @@ class Planner:
     def raw(self, nbytes: int) -> Ref:
         return Ref("ws", self.pool.alloc(nbytes))
 
+    def vt(self, batch: int, Cc: int, ntok: int) -> VT:
+        ld_t = round_up(ntok, 8)
+        n = batch * Cc * ld_t * 2
+        off = self.pool.alloc(2 * n)
+        return VT(Ref("ws", off), Ref("ws", off + n), ld_t)
+
+    def attn(self, q: Planes, q_col: int, k: Planes, k_col: int, vt: VT, out: Planes, *, B: int, heads: int, Nq: int,
+             Nk: int, mask: Optional[Ref], scale: float, kv_bmod: int = 0):
+        self.ops.append(dict(kind="attn", tag=self.tag, q_hi=q.hi, q_lo=q.lo, k_hi=k.hi, k_lo=k.lo, vt_hi=vt.hi, vt_lo=vt.lo,
+                             mask=mask, out_hi=out.hi, out_lo=out.lo, B=B, heads=heads, Nq=Nq, Nk=Nk, ldq=q.Cp, ldk=k.Cp,
+                             ld_t=vt.ld_t, ldo=out.Cp, q_col=q_col, k_col=k_col, kv_bmod=kv_bmod, impl=self.impl, scale=scale))
+
     def free(self, *bufs):
         for b in bufs:
             if b is None:
                 continue
-            r = b.hi if isinstance(b, Planes) else (b.ref if isinstance(b, F32) else b)
+            r = b.hi if isinstance(b, (Planes, VT)) else (b.ref if isinstance(b, F32) else b)
             self.pool.release(r.off)
 
     def mark(self, name: str):
@@ -307,7 +336,7 @@ class Planner:
              res: Optional[F32] = None, res_ref: Optional[Ref] = None, ld_res: Optional[int] = None,
              rowvec: Optional[Ref] = None, ld_rowvec: int = 0, act: int = _lib.ACT_NONE, alpha: float = 1.0,
              accumulate: bool = False, OHF: Optional[int] = None, osy: int = 1, ooy: int = 0,
-             a_off_rows: int = 0, use_bias: bool = True):
+             a_off_rows: int = 0, use_bias: bool = True, qkv=None):
         OH = H if OH is None else OH
         OW = W if OW is None else OW
         assert len(taps) == w.ntaps and a.Cp == w.Cp, (len(taps), w.ntaps, a.Cp, w.Cp)
@@ -320,7 +349,12 @@ class Planner:
                  taps=[(int(dy), int(dx)) for dy, dx in taps], N=w.N, K=w.K, Kpad=w.Kpad, bn=w.bn,
                  ldo=0, ld_res=0, ld_rowvec=ld_rowvec, OHF=OH if OHF is None else OHF, OWF=OW, osy=osy, ooy=ooy,
                  act=act, out_mode=_lib.OUT_F32, accumulate=int(accumulate), splitk=1, impl=self.impl, alpha=alpha)
-        if out_planes is not None:
+        if qkv is not None:          # (planes for columns < n_split, transposed planes for the rest, n_split, tokens per batch)
+            pl_, vt_, n_split, tpb = qkv
+            assert n_split % w.bn == 0 and n_split % 32 == 0 and pl_.Cp == n_split
+            o.update(out_mode=_lib.OUT_QKV, out_hi=pl_.hi, out_lo=pl_.lo, out2_hi=vt_.hi, out2_lo=vt_.lo, ldo=pl_.Cp,
+                     n_split=n_split, tok_per_batch=tpb, ld_t=vt_.ld_t)
+        elif out_planes is not None:
             o["out_mode"] = _lib.OUT_PLANES
             o["out_hi"], o["out_lo"] = out_planes.hi, out_planes.lo
             o["ldo"] = out_planes.Cp if ldo is None else ldo
@@ -417,7 +451,7 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
 
     # ---------------- program 0: conditioning (once per call) ----------------
     P.mark("cond_begin")
-    kv_cache: Dict[str, Tuple[F32, int]] = {}
+    kv_cache: Dict[str, tuple] = {}
     ctx_planes = [P.prep(_lib.PREP_COPY, cb) for cb, _ in ctx_bufs]
     for blk in spec.input_blocks + [spec.middle] + spec.output_blocks:
         for l in blk:
@@ -426,11 +460,12 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
                     n = f"{l.name}.transformer_blocks.{d}.attn2"
                     wkv = torch.cat([sd[n + ".to_k.weight"], sd[n + ".to_v.weight"]], 0).float()
                     wm, taps, cp = packing.conv_weight_matrix(wkv)
-                    w = P.wmat(wm, None, taps, cp)
+                    w = P.wmat(wm, None, taps, cp, bn=P.bn_for_split(2 * l.cin, l.cin))
                     cb, L = ctx_bufs[l.ctx_slot]
-                    kv = F32(P.raw(Bt * L * 2 * l.cin * 4), Bt * L, 2 * l.cin)     # persistent (step-invariant)
-                    P.gemm(ctx_planes[l.ctx_slot], w, B=1, H=Bt * L, out=kv)
-                    kv_cache[n] = (kv, L)
+                    kpl = P.planes(Bt * L, l.cin)                                   # persistent (step-invariant)
+                    vtp = P.vt(Bt, l.cin, L)
+                    P.gemm(ctx_planes[l.ctx_slot], w, B=1, H=Bt * L, qkv=(kpl, vtp, l.cin, L))
+                    kv_cache[n] = (kpl, vtp, L)
     if film is not None:
         yp = P.prep(_lib.PREP_COPY, y_in)
         wf = P.conv_w(sd, "film_emb")
@@ -483,29 +518,27 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
         P.free(p2, skip)
         return out
 
-    def attention(nm: str, h: F32, norm: str, heads: int, Cc: int, HW: int, kv: Optional[Tuple[F32, int]], mask: Optional[Ref]) -> F32:
-        """x = attn(LN(x)) + x  (attention.py:343-367, 406-409)"""
+    def attention(nm: str, h: F32, norm: str, heads: int, Cc: int, HW: int, kv, mask: Optional[Ref]) -> F32:
+        """x = attn(LN(x)) + x  (attention.py:343-367, 406-409).  The projection GEMMs write Q|K as operand
+        planes and V transposed (ALDM_OUT_QKV), which is what the tcgen05 attention kernel consumes."""
         p = P.prep(_lib.PREP_LN, h, None, P.vec(sd[norm + ".weight"]), P.vec(sd[norm + ".bias"]), eps=1e-5)
         ao = P.planes(h.rows, Cc)
-        scale = 32 ** -0.5 if Cc // heads == 32 else (Cc // heads) ** -0.5
+        scale = (Cc // heads) ** -0.5
         if kv is None:
             wq = torch.cat([sd[nm + ".to_q.weight"], sd[nm + ".to_k.weight"], sd[nm + ".to_v.weight"]], 0).float()
             wm, taps, cp = packing.conv_weight_matrix(wq)
-            qkv = P.f32(h.rows, 3 * Cc)
-            P.gemm(p, P.wmat(wm, None, taps, cp), B=1, H=h.rows, out=qkv)
+            qk = P.planes(h.rows, 2 * Cc)
+            vtp = P.vt(Bt, Cc, HW)
+            P.gemm(p, P.wmat(wm, None, taps, cp, bn=P.bn_for_split(3 * Cc, 2 * Cc)), B=1, H=h.rows, qkv=(qk, vtp, 2 * Cc, HW))
             P.free(p)
-            P.ops.append(dict(kind="attn", tag=P.tag, q=qkv.ref, k=qkv.ref + Cc * 4, v=qkv.ref + 2 * Cc * 4, mask=None,
-                              out_hi=ao.hi, out_lo=ao.lo, B=Bt, heads=heads, Nq=HW, Nk=HW, ldq=3 * Cc, ldk=3 * Cc,
-                              ldv=3 * Cc, ldo=Cc, kv_bmod=0, scale=scale))
-            P.free(qkv)
+            P.attn(qk, 0, qk, Cc, vtp, ao, B=Bt, heads=heads, Nq=HW, Nk=HW, mask=None, scale=scale)
+            P.free(qk, vtp)
         else:
-            kvb, L = kv
-            q = P.f32(h.rows, Cc)
-            P.gemm(p, P.conv_w(sd, nm + ".to_q"), B=1, H=h.rows, out=q)
+            kpl, vtp, L = kv
+            q = P.planes(h.rows, Cc)
+            P.gemm(p, P.conv_w(sd, nm + ".to_q"), B=1, H=h.rows, out_planes=q)
             P.free(p)
-            P.ops.append(dict(kind="attn", tag=P.tag, q=q.ref, k=kvb.ref, v=kvb.ref + Cc * 4, mask=mask,
-                              out_hi=ao.hi, out_lo=ao.lo, B=Bt, heads=heads, Nq=HW, Nk=L, ldq=Cc, ldk=2 * Cc,
-                              ldv=2 * Cc, ldo=Cc, kv_bmod=0, scale=scale))
+            P.attn(q, 0, kpl, 0, vtp, ao, B=Bt, heads=heads, Nq=HW, Nk=L, mask=mask, scale=scale)
             P.free(q)
         out = P.f32(h.rows, Cc)
         P.gemm(ao, P.conv_w(sd, nm + ".to_out.0"), B=1, H=h.rows, out=out, res=h)

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define ALDM_ABI_VERSION 3
+#define ALDM_ABI_VERSION 4
 #define ALDM_MAX_TAPS 16
 
 enum {
@@ -65,7 +65,7 @@ enum {
 
 enum { ALDM_GEMM_TC = 0, ALDM_GEMM_SIMT = 1 };                 /* aldm_gemm_desc.impl */
 enum { ALDM_ACT_NONE = 0, ALDM_ACT_GEGLU = 1, ALDM_ACT_TANH = 2, ALDM_ACT_SILU = 3 };
-enum { ALDM_OUT_F32 = 0, ALDM_OUT_PLANES = 1, ALDM_OUT_NCHW = 2 };
+enum { ALDM_OUT_F32 = 0, ALDM_OUT_PLANES = 1, ALDM_OUT_NCHW = 2, ALDM_OUT_QKV = 3 };
 
 /* out[row(m), n] = epilogue( sum_k A[m, k] * W[n, k] ),  k = tap * Cp + c
  * A is gathered from operand planes laid out [B, Hs, Ws, Cp]:
@@ -76,7 +76,11 @@ enum { ALDM_OUT_F32 = 0, ALDM_OUT_PLANES = 1, ALDM_OUT_NCHW = 2 };
  * GEGLU: weights are packed so that tile columns [0,BN/2) are values and [BN/2,BN) their gates;
  *        the stored width is N/2.
  * Output row mapping: orow = (b*OHF + oh*osy + ooy)*OWF + ow ; element = out[orow*ldo + n]
- *        (ALDM_OUT_NCHW: out[((b*N + n)*OH + oh)*OW + ow]). */
+ *        (ALDM_OUT_NCHW: out[((b*N + n)*OH + oh)*OW + ow]).
+ * ALDM_OUT_QKV (attention projections): columns n < n_split go to the planes out_hi/out_lo
+ *        [row m, ldo]; columns n >= n_split (the V projection) are stored TRANSPOSED into
+ *        out2_hi/out2_lo[((m / tok_per_batch) * (N - n_split) + (n - n_split)) * ld_t + m % tok_per_batch]
+ *        so that the attention kernel finds V^T K-major (keys contiguous).  n_split % bn == 0. */
 typedef struct aldm_gemm_desc {
   const void* a_hi;          /* bf16 [B_src, Hs, Ws, Cp] */
   const void* a_lo;
@@ -88,6 +92,8 @@ typedef struct aldm_gemm_desc {
   float* out;                /* fp32 output (ALDM_OUT_F32 / NCHW) */
   void* out_hi;              /* operand-plane output (ALDM_OUT_PLANES), [rows, ldo] bf16 */
   void* out_lo;
+  void* out2_hi;             /* ALDM_OUT_QKV: transposed planes of the columns >= n_split */
+  void* out2_lo;
   float* ws;                 /* split-K workspace [splitk, Mpad, Npad] fp32 or NULL */
   int32_t B, H, W, Cp;       /* logical conv input (after nearest-upsample if up=1) */
   int32_t up, bmod;
@@ -99,6 +105,7 @@ typedef struct aldm_gemm_desc {
   int32_t ldo, ld_res, ld_rowvec;
   int32_t OHF, OWF, osy, ooy;
   int32_t act, out_mode, accumulate, splitk, impl;
+  int32_t n_split, tok_per_batch, ld_t;
   float alpha;
 } aldm_gemm_desc;
 
@@ -135,14 +142,19 @@ int aldm_pack_b(const float* src, int32_t lds, int32_t transpose, int32_t N, int
 /* ---- attention --------------------------------------------------------------------------- */
 
 /* softmax(scale * Q K^T + mask) V per (batch, head), head_dim = 32.
- * Q: [B, Nq, ldq] fp32, head h at columns [h*32, h*32+32); K/V: [Bkv, Nk, ldk]/[.., ldv];
- * kv batch index = b % kv_bmod.  mask: [Bkv, Nk] floats (1 = keep) or NULL; entries != 1 are
- * filled with -FLT_MAX before the softmax exactly like attention.py:356-360.
- * Output: operand planes [B*Nq, ldo]. */
+ * All operands are bf16 hi/lo planes written by the projection GEMMs (ALDM_OUT_QKV / ALDM_OUT_PLANES):
+ *   Q : [B*Nq, ldq], head h at columns [q_col + h*32, +32)
+ *   K : [Bkv*Nk, ldk], head h at columns [k_col + h*32, +32)
+ *   Vt: [(bkv*heads*32 + h*32 + d), ld_t] keys contiguous (V transposed), ld_t >= Nk, ld_t % 8 == 0
+ * kv batch index bkv = b % kv_bmod (0: bkv = b).  mask: [Bkv, Nk] floats (1 = keep) or NULL; entries != 1
+ * are filled with -FLT_MAX before the softmax exactly like attention.py:356-360.
+ * Output: operand planes [B*Nq, ldo], head h at columns [h*32, +32).
+ * impl: ALDM_GEMM_TC = tcgen05 flash kernel, ALDM_GEMM_SIMT = CUDA-core checker. */
 typedef struct aldm_attn_desc {
-  const float* q; const float* k; const float* v; const float* mask;
+  const void* q_hi; const void* q_lo; const void* k_hi; const void* k_lo; const void* vt_hi; const void* vt_lo;
+  const float* mask;
   void* out_hi; void* out_lo;
-  int32_t B, heads, Nq, Nk, ldq, ldk, ldv, ldo, kv_bmod;
+  int32_t B, heads, Nq, Nk, ldq, ldk, ld_t, ldo, q_col, k_col, kv_bmod, impl;
   float scale;
 } aldm_attn_desc;
 
@@ -224,7 +236,7 @@ void aldm_program_destroy(aldm_program* p);
 int aldm_abi_version(void);
 size_t aldm_sizeof_op(void);
 size_t aldm_sizeof_gemm_desc(void);
-size_t aldm_offsetof_gemm(int32_t field);     /* 0:B 1:ntaps 2:dy 3:N 4:ldo 5:act 6:alpha (layout self-check) */
+size_t aldm_offsetof_gemm(int32_t field);     /* 0:B 1:ntaps 2:dy 3:N 4:ldo 5:act 6:alpha 7:n_split (layout self-check) */
 const char* aldm_last_error(void);
 int aldm_device_check(int32_t device);        /* 0 if `device` is sm_100 and kernels can load */
 

@@ -126,19 +126,29 @@ class Emulator:
         B, h, Nq, Nk = o["B"], o["heads"], o["Nq"], o["Nk"]
         d = 32
         Cc = h * d
+        bmod = o["kv_bmod"]
+        Bkv = bmod if bmod > 0 else B
 
-        def grab(ref, rows, ld):
-            # the view may run past the logical end of the last row; only [:, :Cc] is used
-            total = (rows - 1) * ld + Cc
-            flat = self.f32(ref, total)
-            return torch.as_strided(flat, (rows, Cc), (ld, 1))
+        def planes(hi, lo, rows, ld, col):
+            n = (rows - 1) * ld + col + Cc
+            full = self.bf16(hi, n).float() + self.bf16(lo, n).float()
+            return torch.as_strided(full, (rows, Cc), (ld, 1), col)
 
-        q = grab(o["q"], B * Nq, o["ldq"]).reshape(B, Nq, h, d).permute(0, 2, 1, 3)
-        k = grab(o["k"], B * Nk, o["ldk"]).reshape(B, Nk, h, d).permute(0, 2, 1, 3)
-        v = grab(o["v"], B * Nk, o["ldv"]).reshape(B, Nk, h, d).permute(0, 2, 1, 3)
+        q = planes(o["q_hi"], o["q_lo"], B * Nq, o["ldq"], o["q_col"]).reshape(B, Nq, h, d).permute(0, 2, 1, 3)
+        k = planes(o["k_hi"], o["k_lo"], Bkv * Nk, o["ldk"], o["k_col"]).reshape(Bkv, Nk, h, d).permute(0, 2, 1, 3)
+        ld_t = o["ld_t"]
+        nvt = Bkv * Cc * ld_t
+        vt = (self.bf16(o["vt_hi"], nvt).float() + self.bf16(o["vt_lo"], nvt).float()).reshape(Bkv, h, d, ld_t)[..., :Nk]
+        v = vt.permute(0, 1, 3, 2)                                  # [Bkv, h, Nk, d]
+        if bmod > 0:
+            idx = torch.arange(B) % bmod
+            k, v = k[idx], v[idx]
+        assert torch.isfinite(q).all() and torch.isfinite(k).all() and torch.isfinite(v).all(), "attention reads garbage"
         sim = torch.einsum("bhid,bhjd->bhij", q, k) * o["scale"]
         if o.get("mask") is not None:
-            m = self.f32(o["mask"], B * Nk).reshape(B, 1, 1, Nk)
+            m = self.f32(o["mask"], Bkv * Nk).reshape(Bkv, 1, 1, Nk)
+            if bmod > 0:
+                m = m[torch.arange(B) % bmod]
             sim = sim.masked_fill(~(m == 1), -torch.finfo(torch.float32).max)
         out = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), v).permute(0, 2, 1, 3).reshape(B * Nq, Cc)
         self.write_planes(o["out_hi"], o["out_lo"], out, o["ldo"], B * Nq)
@@ -212,6 +222,19 @@ class Emulator:
             if o["accumulate"]:
                 v = v + O[orow]
             O[orow] = v
+        elif mode == _lib.OUT_QKV:
+            ns, tpb, ld_t, ld = o["n_split"], o["tok_per_batch"], o["ld_t"], o["ldo"]
+            a = v[:, :ns]
+            h = a.to(torch.bfloat16); l = (a - h.float()).to(torch.bfloat16)
+            Hh = torch.as_strided(self.bf16(o["out_hi"], (M - 1) * ld + ns), (M, ns), (ld, 1))
+            Ll = torch.as_strided(self.bf16(o["out_lo"], (M - 1) * ld + ns), (M, ns), (ld, 1))
+            Hh[:] = h; Ll[:] = l
+            Cv, nb = N - ns, M // tpb
+            t = v[:, ns:].reshape(nb, tpb, Cv).permute(0, 2, 1)              # [b, c, tok]
+            tp = torch.zeros(nb, Cv, ld_t); tp[:, :, :tpb] = t
+            th = tp.to(torch.bfloat16); tl = (tp - th.float()).to(torch.bfloat16)
+            self.bf16(o["out2_hi"], nb * Cv * ld_t)[:] = th.reshape(-1)
+            self.bf16(o["out2_lo"], nb * Cv * ld_t)[:] = tl.reshape(-1)
         elif mode == _lib.OUT_PLANES:
             ld = o["ldo"]
             h = v.to(torch.bfloat16); l = (v - h.float()).to(torch.bfloat16)

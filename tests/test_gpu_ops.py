@@ -177,33 +177,81 @@ def test_gemm_vs_emulator(case, impl):
     assert err < 2e-5, f"{case}/{impl}: rel L2 {err:.3e}"
 
 
-@pytest.mark.parametrize("case", ["self", "cross_mask", "cross_allmasked", "ragged"])
-def test_attention(case):
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("case", ["self", "self_long", "cross_mask", "cross_allmasked", "ragged", "bmod"])
+def test_attention(case, impl):
+    """Q|K planes + transposed V planes -> attention kernel (tcgen05 / SIMT checker) vs the emulator."""
     g = torch.Generator().manual_seed(5)
-    P = Planner()
+    P = Planner(impl=impl)
     B, heads = 3, 4
     Cc = heads * 32
-    Nq, Nk = (200, 200) if case == "self" else ((70, 9) if case != "ragged" else (33, 130))
-    ldq = 3 * Cc if case == "self" else Cc
-    q = F32(P.raw(B * Nq * ldq * 4), B * Nq, ldq)
-    ao = P.planes(B * Nq, Cc)
-    ios = dict(q=("f32", q.ref, (B * Nq, ldq)))
+    Nq, Nk = dict(self=(200, 200), self_long=(1024, 1024), cross_mask=(70, 9), cross_allmasked=(70, 9), ragged=(33, 130),
+                  bmod=(64, 40))[case]
+    Bkv = 1 if case == "bmod" else B
+    selfattn = case.startswith("self")
+    ldq = 2 * Cc if selfattn else Cc
+    qf = F32(P.raw(B * Nq * ldq * 4), B * Nq, ldq)
+    qp = P.prep(_lib.PREP_COPY, qf)
+    ios = dict(q=("f32", qf.ref, (B * Nq, ldq)))
     ins = dict(q=torch.randn(B * Nq, ldq, generator=g))
-    if case == "self":
-        op = dict(kind="attn", q=q.ref, k=q.ref + Cc * 4, v=q.ref + 2 * Cc * 4, mask=None, Nk=Nq, ldk=ldq, ldv=ldq)
+    vt = P.vt(Bkv, Cc, Nk)
+    mk = None
+    if selfattn:
+        kp, kcol = qp, Cc
     else:
-        kv = F32(P.raw(B * Nk * 2 * Cc * 4), B * Nk, 2 * Cc)
-        mk = P.raw(B * Nk * 4)
-        ios.update(kv=("f32", kv.ref, (B * Nk, 2 * Cc)), mask=("f32", mk, (B, Nk)))
-        m = (torch.rand(B, Nk, generator=g) > 0.4).float(); m[:, 0] = 1
-        if case == "cross_allmasked":
-            m[1] = 0          # fully-masked row -> uniform weights (SURVEY.md 8a' item 5)
-        ins.update(kv=torch.randn(B * Nk, 2 * Cc, generator=g), mask=m)
-        op = dict(kind="attn", q=q.ref, k=kv.ref, v=kv.ref + Cc * 4, mask=mk, Nk=Nk, ldk=2 * Cc, ldv=2 * Cc)
-    op.update(out_hi=ao.hi, out_lo=ao.lo, B=B, heads=heads, Nq=Nq, ldq=ldq, ldo=Cc, kv_bmod=0, scale=32 ** -0.5)
-    P.ops.append(op)
-    em, prog = run_both(P.finish(ios), ins)
-    assert rel_l2(read_gpu_planes(prog, ao), em.read_planes(ao.hi, ao.lo, ao.rows, ao.Cp)) < 2e-5
+        kf = F32(P.raw(Bkv * Nk * Cc * 4), Bkv * Nk, Cc)
+        kp, kcol = P.prep(_lib.PREP_COPY, kf), 0
+        ios["k"] = ("f32", kf.ref, (Bkv * Nk, Cc)); ins["k"] = torch.randn(Bkv * Nk, Cc, generator=g)
+        if case != "ragged":
+            mk = P.raw(Bkv * Nk * 4)
+            m = (torch.rand(Bkv, Nk, generator=g) > 0.4).float(); m[:, 0] = 1
+            if case == "cross_allmasked":
+                m[1] = 0          # fully-masked row -> uniform weights (SURVEY.md 8a' item 5)
+            ios["mask"] = ("f32", mk, (Bkv, Nk)); ins["mask"] = m
+    ao = P.planes(B * Nq, Cc)
+    P.attn(qp, 0, kp, kcol, vt, ao, B=B, heads=heads, Nq=Nq, Nk=Nk, mask=mk, scale=32 ** -0.5,
+           kv_bmod=1 if case == "bmod" else 0)
+    pl = P.finish(ios)
+    # V^T planes are written directly (in the network they come from an ALDM_OUT_QKV GEMM)
+    v = torch.randn(Bkv, Cc, vt.ld_t, generator=g)
+    v[:, :, Nk:] = 0
+    vh = v.to(torch.bfloat16); vl = (v - vh.float()).to(torch.bfloat16)
+    em = Emulator(pl)
+    prog = engine.DeviceProgram(pl, torch.device(DEV), dict(all=(0, len(pl.ops))))
+    n = Bkv * Cc * vt.ld_t
+    em.bf16(vt.hi, n)[:] = vh.reshape(-1); em.bf16(vt.lo, n)[:] = vl.reshape(-1)
+    prog.ws[vt.hi.off:vt.hi.off + 2 * n].view(torch.bfloat16).copy_(vh.reshape(-1))
+    prog.ws[vt.lo.off:vt.lo.off + 2 * n].view(torch.bfloat16).copy_(vl.reshape(-1))
+    for name, val in ins.items():
+        em.write_io(name, val); prog.view(name).copy_(val.to(DEV))
+    em.run(); prog.run("all"); torch.cuda.synchronize()
+    got, want = read_gpu_planes(prog, ao), em.read_planes(ao.hi, ao.lo, ao.rows, ao.Cp)
+    assert torch.isfinite(got).all()
+    err = rel_l2(got, want)
+    assert err < 2e-5, f"{case}/{impl}: {err:.3e}"
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_gemm_qkv_output(impl):
+    """ALDM_OUT_QKV: Q|K columns as planes, V columns as transposed planes (keys contiguous, pad zeroed)."""
+    g = torch.Generator().manual_seed(11)
+    P = Planner(impl=impl, keep_plain=True)
+    Bt, HW, Cc = 3, 37, 64
+    rows = Bt * HW
+    src = F32(P.raw(rows * Cc * 4), rows, Cc)
+    a = P.prep(_lib.PREP_COPY, src)
+    wm = torch.randn(3 * Cc, Cc, generator=g) / 8
+    w = P.wmat(wm, None, 1, Cc, bn=P.bn_for_split(3 * Cc, 2 * Cc))
+    qk = P.planes(rows, 2 * Cc)
+    vt = P.vt(Bt, Cc, HW)
+    P.gemm(a, w, B=1, H=rows, qkv=(qk, vt, 2 * Cc, HW))
+    em, prog = run_both(P.finish(dict(src=("f32", src.ref, (rows, Cc)))), dict(src=torch.randn(rows, Cc, generator=g)))
+    assert rel_l2(read_gpu_planes(prog, qk), em.read_planes(qk.hi, qk.lo, rows, qk.Cp)) < 2e-5
+    n = Bt * Cc * vt.ld_t
+    gv = (prog.ws[vt.hi.off:vt.hi.off + 2 * n].view(torch.bfloat16).float() + prog.ws[vt.lo.off:vt.lo.off + 2 * n].view(torch.bfloat16).float()).cpu()
+    ev = em.bf16(vt.hi, n).float() + em.bf16(vt.lo, n).float()
+    assert torch.isfinite(gv).all() and rel_l2(gv, ev) < 2e-5
+    assert float(gv.reshape(Bt, Cc, vt.ld_t)[:, :, HW:].abs().max()) == 0.0
 
 
 def test_softmax_temb_packb():
