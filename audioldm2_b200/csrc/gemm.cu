@@ -331,6 +331,233 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// persistent variant (default): one CTA per SM loops over output tiles; 320 threads =
+//   warps 0-3 A producers | warp 4 B (TMA bulk) | warp 5 MMA | warps 6-9 epilogue.
+// Two TMEM accumulators (2 x BN columns) let the epilogue of tile i drain while the producers and
+// the tensor core already work on tile i+1; barrier init / TMEM alloc are paid once per CTA.
+// Tile order: split-K slice fastest, then n-tile, then m-tile, so CTAs running concurrently share
+// the same activation rows in L2.
+// ------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n) {
+  using C = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int M = d.B * d.OH * d.OW;
+  const int nkb_total = d.Kpad / C::BK;
+  const int total = tiles_m * tiles_n * d.splitk;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);        // tcgen05.commit after the tile's last k-block
+      mbar_init(tempty_bar(a), 128);     // epilogue threads
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 2 * C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int id, int& mt, int& nt, int& z, int& kb0, int& nkb) {
+    z = id % d.splitk;
+    const int r = id / d.splitk;
+    nt = r % tiles_n;
+    mt = r / tiles_n;
+    kb0 = (int)(((long long)z * nkb_total) / d.splitk);
+    nkb = (int)(((long long)(z + 1) * nkb_total) / d.splitk) - kb0;
+  };
+
+  if (warp < 4) {
+    // ===================== A producers =====================
+    const int j = tid & 7;
+    const int rbase = tid >> 3;
+    const uint32_t swz = (uint32_t)((j ^ (rbase & 7)) << 4);
+    const int Hs = d.H >> d.up, Ws = d.W >> d.up;
+    const __nv_bfloat16* ahi = reinterpret_cast<const __nv_bfloat16*>(d.a_hi);
+    const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(d.a_lo);
+    uint32_t cnt = 0;
+    int last_mt = -1;
+    int ih0[8], iw0[8], pb[8];
+    for (int id = blockIdx.x; id < total; id += gridDim.x) {
+      int mt, nt, z, kb0, nkb;
+      tile_coords(id, mt, nt, z, kb0, nkb);
+      if (mt != last_mt) {
+        last_mt = mt;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = mt * C::BM + rbase + 16 * i;
+          if (m < M) {
+            const int ow = m % d.OW;
+            const int t = m / d.OW;
+            const int oh = t % d.OH;
+            const int b = t / d.OH;
+            ih0[i] = oh * d.sy;
+            iw0[i] = ow * d.sx;
+            pb[i] = (d.bmod > 0 ? b % d.bmod : b) * Hs;
+          } else {
+            ih0[i] = 0; iw0[i] = 0; pb[i] = -1;
+          }
+        }
+      }
+      for (int it = 0; it < nkb; ++it, ++cnt) {
+        const int s = cnt % C::STAGES;
+        mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+        const int k = (kb0 + it) * C::BK + j * 8;
+        const bool kvalid = k < d.K;
+        int tap = 0, c = 0;
+        if (kvalid) { tap = k / d.Cp; c = k - tap * d.Cp; }
+        const int dy = d.dy[tap], dx = d.dx[tap];
+        const uint32_t sa = base + s * C::STAGE_BYTES + swz;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ih = ih0[i] + dy, iw = iw0[i] + dx;
+          const bool ok = kvalid && pb[i] >= 0 && ih >= 0 && ih < d.H && iw >= 0 && iw < d.W;
+          long long off = 0;
+          if (ok) off = ((long long)(pb[i] + (ih >> d.up)) * Ws + (iw >> d.up)) * d.Cp + c;
+          const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
+          cp_async_16(dst, ahi + off, ok ? 16u : 0u);
+          cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(full_bar(s));
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== B producer =====================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int id = blockIdx.x; id < total; id += gridDim.x) {
+        int mt, nt, z, kb0, nkb;
+        tile_coords(id, mt, nt, z, kb0, nkb);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(d.w_packed) + ((long long)nt * nkb_total + kb0) * (2 * C::B_BYTES);
+        for (int it = 0; it < nkb; ++it, ++cnt) {
+          const int s = cnt % C::STAGES;
+          mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
+          bulk_g2s(base + s * C::STAGE_BYTES + 2 * C::A_BYTES, wsrc + (long long)it * (2 * C::B_BYTES), 2 * C::B_BYTES,
+                   full_bar(s));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      uint32_t cnt = 0, tl = 0;
+      for (int id = blockIdx.x; id < total; id += gridDim.x, ++tl) {
+        int mt, nt, z, kb0, nkb;
+        tile_coords(id, mt, nt, z, kb0, nkb);
+        const uint32_t acc = tl & 1;
+        mbar_wait(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int it = 0; it < nkb; ++it, ++cnt) {
+          const int s = cnt % C::STAGES;
+          mbar_wait(full_bar(s), (cnt / C::STAGES) & 1);
+          tc_fence_after();
+          fence_proxy_async();
+          const uint32_t sa = base + s * C::STAGE_BYTES;
+          const uint64_t da_hi = umma_desc_sw128(sa);
+          const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);
+          const uint64_t db_hi = umma_desc_sw128(sa + 2 * C::A_BYTES);
+          const uint64_t db_lo = umma_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t o = (uint64_t)(ks * 2);
+            umma_bf16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
+            umma_bf16(tacc, da_hi + o, db_lo + o, idesc, 1);
+            umma_bf16(tacc, da_hi + o, db_hi + o, idesc, 1);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 6-9; TMEM lane block = warp % 4) =====================
+    const int lb = warp & 3;
+    const int trow_in_tile = lb * 32 + lane;
+    uint32_t tl = 0;
+    for (int id = blockIdx.x; id < total; id += gridDim.x, ++tl) {
+      int mt, nt, z, kb0, nkb;
+      tile_coords(id, mt, nt, z, kb0, nkb);
+      const uint32_t acc = tl & 1;
+      mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
+      tc_fence_after();
+      const int m = mt * C::BM + trow_in_tile;
+      const RowInfo r = decode_row(d, m, M);
+      const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(lb * 32) << 16);
+      if (d.splitk > 1) {
+        const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
+        float* wp = d.ws + ((long long)z * Mpad + m) * Npad + nt * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(trow + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<uint4*>(wp + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      } else if (d.act == ALDM_ACT_GEGLU) {
+        const int n_out = d.N / 2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          uint32_t vr[32], gr[32];
+          tmem_ld32(trow + c0, vr);
+          tmem_ld32(trow + BN / 2 + c0, gr);
+          tmem_ld_wait();
+          float* v = reinterpret_cast<float*>(vr);
+          float* g = reinterpret_cast<float*>(gr);
+          epi_activate(d, r, nt * BN + c0, v, g);
+          epi_finish(d, r, nt * (BN / 2) + c0, 32, v, n_out);
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t vr[32];
+          tmem_ld32(trow + c0, vr);
+          tmem_ld_wait();
+          float* v = reinterpret_cast<float*>(vr);
+          epi_activate(d, r, nt * BN + c0, v, nullptr);
+          epi_finish(d, r, nt * BN + c0, 32, v, d.N);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // split-K reduction + epilogue
 // ------------------------------------------------------------------------------------------
 __global__ void splitk_epilogue_kernel(const __grid_constant__ aldm_gemm_desc d, int Mpad, int Npad) {
@@ -451,7 +678,37 @@ static int launch_tc(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   return ALDM_OK;
 }
 
-int gemm_num_launches(const aldm_gemm_desc& d) { return (d.impl == ALDM_GEMM_TC && d.splitk > 1) ? 2 : 1; }
+static int g_num_sms = 0;
+
+template <int BN>
+static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
+  using C = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    ALDM_CHECK_CUDA(cudaGetDevice(&dev));
+    ALDM_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles_m = cdiv(M, C::BM), tiles_n = cdiv(d.N, BN);
+  const long long total = (long long)tiles_m * tiles_n * d.splitk;
+  const int grid = (int)(total < g_num_sms ? total : g_num_sms);
+  gemm_tc2_kernel<BN><<<grid, 320, C::SMEM_BYTES, st>>>(d, tiles_m, tiles_n);
+  ALDM_CHECK_CUDA(cudaGetLastError());
+  if (d.splitk > 1) {
+    const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
+    const int chunks = (d.act == ALDM_ACT_GEGLU) ? (Npad / BN) * (BN / 64) : Npad / 32;
+    const long long tot = (long long)M * chunks;
+    splitk_epilogue_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d, Mpad, Npad);
+    ALDM_CHECK_CUDA(cudaGetLastError());
+  }
+  return ALDM_OK;
+}
+
+int gemm_num_launches(const aldm_gemm_desc& d) { return (d.impl != ALDM_GEMM_SIMT && d.splitk > 1) ? 2 : 1; }
 
 int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
   const long long Mll = (long long)d.B * d.OH * d.OW;
@@ -495,10 +752,17 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
     return ALDM_OK;
   }
   ALDM_REQUIRE(d.w_packed && aligned16(d.w_packed), ALDM_E_ARG, "gemm: w_packed null/unaligned");
+  if (d.impl == ALDM_GEMM_TC_V1) {
+    switch (d.bn) {
+      case 128: return launch_tc<128>(d, M, st);
+      case 64: return launch_tc<64>(d, M, st);
+      default: return launch_tc<32>(d, M, st);
+    }
+  }
   switch (d.bn) {
-    case 128: return launch_tc<128>(d, M, st);
-    case 64: return launch_tc<64>(d, M, st);
-    default: return launch_tc<32>(d, M, st);
+    case 128: return launch_tc2<128>(d, M, st);
+    case 64: return launch_tc2<64>(d, M, st);
+    default: return launch_tc2<32>(d, M, st);
   }
 }
 

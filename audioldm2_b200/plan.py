@@ -226,9 +226,9 @@ class Plan:
 
 class Planner:
     def __init__(self, impl: str = "tc", keep_plain: bool = False, splitk: bool = True, n_sm: int = 148):
-        self.impl = _lib.GEMM_TC if impl == "tc" else _lib.GEMM_SIMT
-        self.keep_plain = keep_plain or impl != "tc"
-        self.use_splitk = splitk and impl == "tc"
+        self.impl = {"tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT, "tc1": _lib.GEMM_TC_V1}[impl]
+        self.keep_plain = keep_plain or impl == "simt"
+        self.use_splitk = splitk and impl != "simt"
         self.n_sm = n_sm
         self.arena = Arena()
         self.pool = Pool()

@@ -41,7 +41,7 @@ def test_enum_values_match_header():
         m = re.search(r"\b" + name + r"\s*=\s*(-?\d+)", hdr)
         assert m, name
         return int(m.group(1))
-    assert val("ALDM_GEMM_TC") == _lib.GEMM_TC and val("ALDM_GEMM_SIMT") == _lib.GEMM_SIMT
+    assert val("ALDM_GEMM_TC") == _lib.GEMM_TC and val("ALDM_GEMM_SIMT") == _lib.GEMM_SIMT and val("ALDM_GEMM_TC_V1") == _lib.GEMM_TC_V1
     assert [val("ALDM_ACT_NONE"), val("ALDM_ACT_GEGLU"), val("ALDM_ACT_TANH"), val("ALDM_ACT_SILU")] == [0, 1, 2, 3]
     assert [val("ALDM_OUT_F32"), val("ALDM_OUT_PLANES"), val("ALDM_OUT_NCHW")] == [0, 1, 2]
     assert [val("ALDM_PREP_" + n) for n in ("COPY", "SILU", "LRELU", "GN", "GN_SILU", "LN")] == [0, 1, 2, 3, 4, 5]
