@@ -110,20 +110,25 @@ __device__ __forceinline__ void epi_finish(const aldm_gemm_desc& d, const RowInf
 
 // Bias / rowvec / activation for one 32-column chunk whose packed column base is pc0.
 // For GEGLU `g` holds the gate chunk (packed columns pc0 + bn/2 ...).
+__device__ __forceinline__ void add_vec32(float* v, const float* __restrict__ p) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+      v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __ldg(p + i);
+  }
+}
+
 __device__ __forceinline__ void epi_activate(const aldm_gemm_desc& d, const RowInfo& r, int pc0, float* v, float* g) {
   if (d.bias) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += __ldg(d.bias + pc0 + i);
-    if (d.act == ALDM_ACT_GEGLU) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) g[i] += __ldg(d.bias + pc0 + d.bn / 2 + i);
-    }
+    add_vec32(v, d.bias + pc0);
+    if (d.act == ALDM_ACT_GEGLU) add_vec32(g, d.bias + pc0 + d.bn / 2);
   }
-  if (d.rowvec) {
-    const float* rv = d.rowvec + (long long)r.b * d.ld_rowvec + pc0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += __ldg(rv + i);
-  }
+  if (d.rowvec) add_vec32(v, d.rowvec + (long long)r.b * d.ld_rowvec + pc0);
   if (d.act == ALDM_ACT_GEGLU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= gelu_f(g[i]);
@@ -134,6 +139,59 @@ __device__ __forceinline__ void epi_activate(const aldm_gemm_desc& d, const RowI
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
   }
+}
+
+// Coalesced finish: the 32x32 chunk (lane == row) is transposed through a per-warp shared-memory
+// staging tile (stride 33: conflict-free both ways) so that 8 lanes cover one 128-byte output row
+// segment: residual loads and output stores are full-line float4 transactions instead of 32
+// scattered 16-byte pieces.  Handles fp32 and operand-plane outputs; returns false if the layout
+// does not allow it (caller falls back to the row-owner path).
+__device__ __forceinline__ bool epi_coalescable(const aldm_gemm_desc& d, int n_out) {
+  if (n_out % 4 != 0 || d.ldo % 4 != 0) return false;
+  if (d.res && d.ld_res % 4 != 0) return false;
+  return d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_PLANES || d.out_mode == ALDM_OUT_QKV;
+}
+
+__device__ __forceinline__ void epi_finish_coalesced(const aldm_gemm_desc& d, const RowInfo& r, int n0, const float* v,
+                                                     int n_out, float* stg, int lane) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
+  __syncwarp();
+  const unsigned vmask = __ballot_sync(0xffffffffu, r.valid);
+  const int rs = lane >> 3, c4 = (lane & 7) * 4;
+  const int n = n0 + c4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rs;
+    const long long orow = __shfl_sync(0xffffffffu, r.orow, rr);
+    if (!((vmask >> rr) & 1u) || n >= n_out) continue;
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = stg[rr * 33 + c4 + i];
+    if (d.res) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(d.res + orow * d.ld_res + n));
+      x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+    }
+    if (d.alpha != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] *= d.alpha;
+    }
+    if (d.out_mode == ALDM_OUT_F32) {
+      float4* op = reinterpret_cast<float4*>(d.out + orow * d.ldo + n);
+      if (d.accumulate) {
+        const float4 t = *op;
+        x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+      }
+      *op = make_float4(x[0], x[1], x[2], x[3]);
+    } else {
+      uint2 h, l;
+      split2(x[0], x[1], h.x, l.x);
+      split2(x[2], x[3], h.y, l.y);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + n) = h;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + n) = l;
+    }
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -148,6 +206,8 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STG_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose staging (persistent kernel)
+  static constexpr int SMEM2_BYTES = SMEM_BYTES + STG_BYTES;
   static constexpr int TMEM_COLS = BN;                // power of two >= 32
 };
 
@@ -499,6 +559,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     // ===================== epilogue (warps 6-9; TMEM lane block = warp % 4) =====================
     const int lb = warp & 3;
     const int trow_in_tile = lb * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)) + lb * (32 * 33);
     uint32_t tl = 0;
     for (int id = blockIdx.x; id < total; id += gridDim.x, ++tl) {
       int mt, nt, z, kb0, nkb;
@@ -510,19 +571,28 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       const RowInfo r = decode_row(d, m, M);
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(lb * 32) << 16);
       if (d.splitk > 1) {
+        // raw partial sums -> ws[z][m][n], coalesced through the staging tile
         const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
-        float* wp = d.ws + ((long long)z * Mpad + m) * Npad + nt * BN;
+        const int rs = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(trow + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<uint4*>(wp + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(v[i]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rs;
+            float* wp = d.ws + ((long long)z * Mpad + mt * C::BM + lb * 32 + rr) * Npad + nt * BN + c0 + c4;
+            *reinterpret_cast<float4*>(wp) = make_float4(stg[rr * 33 + c4], stg[rr * 33 + c4 + 1], stg[rr * 33 + c4 + 2], stg[rr * 33 + c4 + 3]);
+          }
+          __syncwarp();
         }
       } else if (d.act == ALDM_ACT_GEGLU) {
         const int n_out = d.N / 2;
+        const bool co = epi_coalescable(d, n_out);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 2; c0 += 32) {
           uint32_t vr[32], gr[32];
@@ -532,17 +602,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           float* v = reinterpret_cast<float*>(vr);
           float* g = reinterpret_cast<float*>(gr);
           epi_activate(d, r, nt * BN + c0, v, g);
-          epi_finish(d, r, nt * (BN / 2) + c0, 32, v, n_out);
+          if (co) epi_finish_coalesced(d, r, nt * (BN / 2) + c0, v, n_out, stg, lane);
+          else epi_finish(d, r, nt * (BN / 2) + c0, 32, v, n_out);
         }
       } else {
+        const bool co = epi_coalescable(d, d.N);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t vr[32];
           tmem_ld32(trow + c0, vr);
           tmem_ld_wait();
           float* v = reinterpret_cast<float*>(vr);
-          epi_activate(d, r, nt * BN + c0, v, nullptr);
-          epi_finish(d, r, nt * BN + c0, 32, v, d.N);
+          const int n0 = nt * BN + c0;
+          epi_activate(d, r, n0, v, nullptr);
+          if (co && !(d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split)) epi_finish_coalesced(d, r, n0, v, d.N, stg, lane);
+          else epi_finish(d, r, n0, 32, v, d.N);
         }
       }
       tc_fence_before();
@@ -685,7 +759,7 @@ static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   using C = TcCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM2_BYTES));
     configured = true;
   }
   if (g_num_sms == 0) {
@@ -696,7 +770,7 @@ static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   const int tiles_m = cdiv(M, C::BM), tiles_n = cdiv(d.N, BN);
   const long long total = (long long)tiles_m * tiles_n * d.splitk;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  gemm_tc2_kernel<BN><<<grid, 320, C::SMEM_BYTES, st>>>(d, tiles_m, tiles_n);
+  gemm_tc2_kernel<BN><<<grid, 320, C::SMEM2_BYTES, st>>>(d, tiles_m, tiles_n);
   ALDM_CHECK_CUDA(cudaGetLastError());
   if (d.splitk > 1) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
