@@ -368,8 +368,10 @@ class Planner:
         if self.use_splitk:
             tiles = math.ceil(M / 128) * math.ceil(w.N / w.bn)
             nkb = w.Kpad // 64
-            if tiles * 2 <= self.n_sm and nkb >= 8:
-                sk = min(nkb // 4, max(1, self.n_sm // tiles), 16)
+            # only worth a second (reduction) kernel when the K loop is long: a short loop is dominated by
+            # fixed per-tile costs either way
+            if tiles * 2 <= self.n_sm and nkb >= 24:
+                sk = min(nkb // 8, max(1, self.n_sm // tiles), 16)
                 if sk > 1:
                     o["splitk"] = sk
                     need = sk * round_up(M, 128) * round_up(w.N, w.bn) * 4
