@@ -71,20 +71,39 @@ def model_config(model_name: str = "audioldm2-full") -> dict:
                 linear_start=0.0015, linear_end=0.0195, timesteps=1000)
 
 
-def tiny_config(film: bool = False) -> dict:
-    """A shrunken config with the same topology (used by fast CPU tests)."""
+def tiny_config(film: bool = False, variant: str = "") -> dict:
+    """Shrunken configs with the same topology as the real ones (fast parity tests).
+
+    variant "" / film : audioldm2-full topology (3 STs per site) / audioldm_48k UNet topology (FiLM, 2 self-attn STs)
+    variant "large"   : audioldm2-full-large topology: context_dim [.., .., None], transformer_depth 2 (utils.py:118-120)
+    variant "48k"     : audioldm_48k first stage: 4-level VAE (ch_mult [1,2,4,8]), HiFi-GAN with 4 MRF kernels
+                        (3,7,11,15) and the 48 k upsampling plan (6,5,4,2,2) (utils.py:475-493, utilities/model.py:39-75)
+    """
     unet = dict(_UNET_BASE)
     unet.update(model_channels=32, context_dim=[48, 64])
     if film:
         unet.update(context_dim=[None], extra_film_condition_dim=24)
+    if variant == "large":
+        unet.update(context_dim=[48, 64, None], transformer_depth=2)
     vae = dict(ch=32, ch_mult=[1, 2, 4], num_res_blocks=1, z_channels=8, in_channels=1,
                out_ch=1, embed_dim=8, double_z=True, mel_bins=32)
     voc = dict(upsample_rates=[5, 4, 2, 2, 2], upsample_kernel_sizes=[16, 16, 8, 4, 4],
                upsample_initial_channel=128, resblock_kernel_sizes=[3, 7, 11],
                resblock_dilation_sizes=[[1, 3, 5]] * 3, num_mels=32,
                n_fft=256, hop_size=40, win_size=256, sampling_rate=4000, fmin=0, fmax=2000)
-    return dict(name="tiny-film" if film else "tiny", unet=unet, vae=vae, vocoder=voc,
-                latent=(8, 32, 8), sampling_rate=4000, latent_t_per_second=25.6,
+    latent = (8, 32, 8)
+    if variant == "48k":
+        unet.update(in_channels=16, out_channels=16, context_dim=[None], extra_film_condition_dim=24)
+        vae = dict(ch=32, ch_mult=[1, 2, 4, 8], num_res_blocks=1, z_channels=16, in_channels=1,
+                   out_ch=1, embed_dim=16, double_z=True, mel_bins=64)
+        voc = dict(upsample_rates=[6, 5, 4, 2, 2], upsample_kernel_sizes=[12, 10, 8, 4, 4],
+                   upsample_initial_channel=192, resblock_kernel_sizes=[3, 7, 11, 15],
+                   resblock_dilation_sizes=[[1, 3, 5]] * 4, num_mels=64,
+                   n_fft=256, hop_size=40, win_size=256, sampling_rate=4000, fmin=0, fmax=2000)
+        latent = (16, 16, 8)
+    name = "tiny" + ("-film" if film else "") + (("-" + variant) if variant else "")
+    return dict(name=name, unet=unet, vae=vae, vocoder=voc,
+                latent=latent, sampling_rate=4000, latent_t_per_second=25.6,
                 linear_start=0.0015, linear_end=0.0195, timesteps=1000)
 
 

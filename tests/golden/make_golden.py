@@ -162,7 +162,12 @@ def main():
     torch.set_num_threads(os.cpu_count())
     R = ref_loader.load()
     full, tiny, tinyf = arch.model_config("audioldm2-full"), arch.tiny_config(), arch.tiny_config(film=True)
+    tinyl, tiny48 = arch.tiny_config(variant="large"), arch.tiny_config(variant="48k")
     jobs = {
+        "unet_tiny_large": lambda: gen_unet(R, "unet_tiny_large", tinyl, 2, t5_len=5),
+        "unet_tiny_48k": lambda: gen_unet(R, "unet_tiny_48k", tiny48, 2),
+        "vae_tiny_48k": lambda: gen_vae(R, "vae_tiny_48k", tiny48, 2),
+        "vocoder_tiny_48k": lambda: gen_vocoder(R, "vocoder_tiny_48k", tiny48, 2, 16),
         "unet_tiny": lambda: gen_unet(R, "unet_tiny", tiny, 2, t5_len=5),
         "unet_tiny_film": lambda: gen_unet(R, "unet_tiny_film", tinyf, 2),
         "vae_tiny": lambda: gen_vae(R, "vae_tiny", tiny, 2),

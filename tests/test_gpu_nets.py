@@ -60,6 +60,38 @@ def test_unet_tiny_film():
     assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL and rel_l2(e_c, g["eps_cond"]) < NET_TOL
 
 
+def test_unet_tiny_large_topology():
+    cfg = arch.tiny_config(variant="large")
+    eng = _engine(cfg, 2, 5)
+    g = cases.load("unet_tiny_large")
+    x, t, cond, unc = cases.unet_inputs(cfg, 2, t5_len=5)
+    eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
+    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL and rel_l2(e_c, g["eps_cond"]) < NET_TOL
+
+
+def test_tiny_48k_topology():
+    """audioldm_48k: FiLM UNet (16-ch latent), 4-level VAE decoder/encoder, 48 k HiFi-GAN plan (k up to 15)."""
+    from audioldm2_b200 import engine, plan
+    cfg = arch.tiny_config(variant="48k")
+    eng = _engine(cfg, 2, 32, with_encoder=True)
+    g = cases.load("unet_tiny_48k")
+    x, t, cond, unc = cases.unet_inputs(cfg, 2)
+    eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
+    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL and rel_l2(e_c, g["eps_cond"]) < NET_TOL
+    gv = cases.load("vae_tiny_48k")
+    assert rel_l2(eng.decode_first_stage(cases.latent(cfg, 2, seed=5).to(DEV)), gv["mel"]) < NET_TOL
+    mom = eng.encode_first_stage_moments(cases.mel_input(cfg, 2).to(DEV))
+    assert rel_l2(mom.permute(0, 3, 1, 2), gv["moments"]) < NET_TOL
+    gw = cases.load("vocoder_tiny_48k")
+    pv = plan.build_vocoder(synth.vocoder_state_dict(cfg["vocoder"]), cfg["vocoder"], 16, 2)
+    prog = engine.DeviceProgram(pv, torch.device(DEV), dict(all=(0, len(pv.ops))))
+    prog.view("mel").copy_(cases.vocoder_input(cfg, 2, 16).permute(0, 2, 1).contiguous().to(DEV))
+    prog.run("all")
+    assert rel_l2(prog.view("wave"), gw["wave"]) < NET_TOL
+
+
 def test_vae_and_vocoder_tiny(tiny_tc):
     cfg = arch.tiny_config()
     g = cases.load("vae_tiny")

@@ -15,9 +15,10 @@ from tests.golden import cases
 TOL = 2e-5
 
 
-@pytest.mark.parametrize("name,film,t5", [("unet_tiny", False, 5), ("unet_tiny_film", True, 32)])
-def test_unet_tiny(name, film, t5):
-    cfg = arch.tiny_config(film=film)
+@pytest.mark.parametrize("name,film,t5,variant", [("unet_tiny", False, 5, ""), ("unet_tiny_film", True, 32, ""),
+                                                  ("unet_tiny_large", False, 5, "large"), ("unet_tiny_48k", False, 32, "48k")])
+def test_unet_tiny(name, film, t5, variant):
+    cfg = arch.tiny_config(film=film, variant=variant)
     g = cases.load(name)
     sd = synth.unet_state_dict(cfg["unet"])
     x, t, cond, unc = cases.unet_inputs(cfg, 2, t5_len=t5)
@@ -36,6 +37,18 @@ def test_vae_tiny():
         mom = OF.vae_encode_moments(sd, cfg["vae"], cases.mel_input(cfg, 2))
     assert rel_l2(mel, g["mel"]) < TOL
     assert rel_l2(mom, g["moments"]) < TOL
+
+
+def test_first_stage_tiny_48k_topology():
+    cfg = arch.tiny_config(variant="48k")
+    g = cases.load("vae_tiny_48k")
+    sd = synth.vae_state_dict(cfg["vae"])
+    with torch.no_grad():
+        assert rel_l2(OF.vae_decode(sd, cfg["vae"], cases.latent(cfg, 2, seed=5)), g["mel"]) < TOL
+        assert rel_l2(OF.vae_encode_moments(sd, cfg["vae"], cases.mel_input(cfg, 2)), g["moments"]) < TOL
+        gv = cases.load("vocoder_tiny_48k")
+        w = OF.vocoder_forward(synth.vocoder_state_dict(cfg["vocoder"]), cfg["vocoder"], cases.vocoder_input(cfg, 2, 16))
+    assert rel_l2(w, gv["wave"]) < TOL
 
 
 def test_vocoder_tiny():

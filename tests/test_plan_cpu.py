@@ -57,6 +57,7 @@ def test_conv_transpose_phases_match_torch():
 
 
 def _run_unet(cfg, B, t5_len, fixture, film=False):
+    film = film or cfg["unet"].get("extra_film_condition_dim") is not None
     sd = synth.unet_state_dict(cfg["unet"])
     x, t, cond, unc = cases.unet_inputs(cfg, B, t5_len=t5_len)
     lens = tuple(c.shape[1] for c in cond["context_list"]) or (8,)
@@ -91,6 +92,30 @@ def test_unet_tiny_plan():
 
 def test_unet_tiny_film_plan():
     _run_unet(arch.tiny_config(film=True), 2, 32, "unet_tiny_film", film=True)
+
+
+def test_unet_tiny_large_plan():
+    """audioldm2-full-large topology: 4 STs per site (last one self-attention), transformer_depth 2."""
+    _run_unet(arch.tiny_config(variant="large"), 2, 5, "unet_tiny_large")
+
+
+def test_tiny_48k_plans():
+    """audioldm_48k topology: FiLM UNet on a 16-channel latent, 4-level VAE, HiFi-GAN with 4 MRF kernels (k=15)."""
+    cfg = arch.tiny_config(variant="48k")
+    _run_unet(cfg, 2, 32, "unet_tiny_48k")
+    sd = synth.vae_state_dict(cfg["vae"])
+    g = cases.load("vae_tiny_48k")
+    pl = plan.build_vae_decoder(sd, cfg["vae"], cfg["latent"], 2, keep_plain=True)
+    em = Emulator(pl); em.write_io("z", cases.latent(cfg, 2, seed=5)); em.run()
+    assert rel_l2(em.read_io("mel"), g["mel"]) < TOL
+    mel = cases.mel_input(cfg, 2)
+    pl = plan.build_vae_encoder(sd, cfg["vae"], tuple(mel.shape[2:]), 2, keep_plain=True)
+    em = Emulator(pl); em.write_io("mel", mel); em.run()
+    assert rel_l2(em.read_io("moments").permute(0, 3, 1, 2), g["moments"]) < TOL
+    gv = cases.load("vocoder_tiny_48k")
+    pl = plan.build_vocoder(synth.vocoder_state_dict(cfg["vocoder"]), cfg["vocoder"], 16, 2, keep_plain=True)
+    em = Emulator(pl); em.write_io("mel", cases.vocoder_input(cfg, 2, 16).permute(0, 2, 1).contiguous()); em.run()
+    assert rel_l2(em.read_io("wave"), gv["wave"]) < TOL
 
 
 def test_vae_tiny_plans():
