@@ -64,6 +64,15 @@ __device__ __forceinline__ void epi_finish(const aldm_gemm_desc& d, const RowInf
     } else {
       for (int i = 0; i < cnt; ++i) op[i] = v[i];
     }
+    if (d.out_hi) {   // dual output: the same values also as operand planes for the next GEMM
+      __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + r.orow * d.ldo + n0;
+      __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + r.orow * d.ldo + n0;
+      for (int i = 0; i < cnt; ++i) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+        hp[i] = h;
+        lp[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+      }
+    }
   } else if (d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split) {
     // V projection: transposed planes [(b*Cv + c), ld_t] with the token index contiguous
     const int b = r.m / d.tok_per_batch, tok = r.m - b * d.tok_per_batch;
@@ -183,7 +192,8 @@ __device__ __forceinline__ void epi_finish_coalesced(const aldm_gemm_desc& d, co
         x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
       }
       *op = make_float4(x[0], x[1], x[2], x[3]);
-    } else {
+    }
+    if (d.out_mode != ALDM_OUT_F32 || d.out_hi) {
       uint2 h, l;
       split2(x[0], x[1], h.x, l.x);
       split2(x[2], x[3], h.y, l.y);

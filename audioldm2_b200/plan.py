@@ -336,7 +336,7 @@ class Planner:
              res: Optional[F32] = None, res_ref: Optional[Ref] = None, ld_res: Optional[int] = None,
              rowvec: Optional[Ref] = None, ld_rowvec: int = 0, act: int = _lib.ACT_NONE, alpha: float = 1.0,
              accumulate: bool = False, OHF: Optional[int] = None, osy: int = 1, ooy: int = 0,
-             a_off_rows: int = 0, use_bias: bool = True, qkv=None):
+             a_off_rows: int = 0, use_bias: bool = True, qkv=None, also_planes: Optional[Planes] = None):
         OH = H if OH is None else OH
         OW = W if OW is None else OW
         assert len(taps) == w.ntaps and a.Cp == w.Cp, (len(taps), w.ntaps, a.Cp, w.Cp)
@@ -362,6 +362,9 @@ class Planner:
             o["out_mode"] = _lib.OUT_F32 if out_mode is None else out_mode
             o["out"] = out.ref if out is not None else out_ref
             o["ldo"] = (out.C if out is not None else n_out) if ldo is None else ldo
+            if also_planes is not None:       # dual output: fp32 + operand planes with the same leading dimension
+                assert also_planes.Cp == o["ldo"] and o["out_mode"] == _lib.OUT_F32
+                o["out_hi"], o["out_lo"] = also_planes.hi, also_planes.lo
         if o["res"] is not None:
             o["ld_res"] = (res.C if res is not None else n_out) if ld_res is None else ld_res
         # split-K for tiles that cannot fill the machine (deep UNet levels at small batch)
@@ -568,9 +571,11 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
                    act=_lib.ACT_GEGLU)
             P.free(p)
             h2 = P.f32(h.rows, Cc)
-            P.gemm(g, P.conv_w(sd, b + ".ff.net.2"), B=1, H=h.rows, out=h2, res=h)
+            last = d == l.depth - 1
+            hp = P.planes(h.rows, Cc) if last else None      # proj_out's operand, written by the same epilogue
+            P.gemm(g, P.conv_w(sd, b + ".ff.net.2"), B=1, H=h.rows, out=h2, res=h, also_planes=hp)
             P.free(g, h); h = h2
-        p = P.prep(_lib.PREP_COPY, h); P.free(h)
+        p = hp; P.free(h)
         out = P.f32(x.rows, Cc)
         P.gemm(p, P.conv_w(sd, n + ".proj_out"), B=Bt, H=H, W=W, out=out, res=x)
         P.free(p)

@@ -77,6 +77,8 @@ enum { ALDM_OUT_F32 = 0, ALDM_OUT_PLANES = 1, ALDM_OUT_NCHW = 2, ALDM_OUT_QKV = 
  *        the stored width is N/2.
  * Output row mapping: orow = (b*OHF + oh*osy + ooy)*OWF + ow ; element = out[orow*ldo + n]
  *        (ALDM_OUT_NCHW: out[((b*N + n)*OH + oh)*OW + ow]).
+ * ALDM_OUT_F32 with out_hi/out_lo != NULL: dual output, the values are additionally stored as operand
+ *        planes [orow, ldo] (saves the copy-prep kernel in front of the next GEMM).
  * ALDM_OUT_QKV (attention projections): columns n < n_split go to the planes out_hi/out_lo
  *        [row m, ldo]; columns n >= n_split (the V projection) are stored TRANSPOSED into
  *        out2_hi/out2_lo[((m / tok_per_batch) * (N - n_split) + (n - n_split)) * ld_t + m % tok_per_batch]

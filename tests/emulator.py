@@ -222,6 +222,11 @@ class Emulator:
             if o["accumulate"]:
                 v = v + O[orow]
             O[orow] = v
+            if o.get("out_hi") is not None:      # dual output (fp32 + operand planes)
+                h = v.to(torch.bfloat16); l = (v - h.float()).to(torch.bfloat16)
+                Hh = torch.as_strided(self.bf16(o["out_hi"], (nrows_out - 1) * ld + n_out), (nrows_out, n_out), (ld, 1))
+                Ll = torch.as_strided(self.bf16(o["out_lo"], (nrows_out - 1) * ld + n_out), (nrows_out, n_out), (ld, 1))
+                Hh[orow] = h; Ll[orow] = l
         elif mode == _lib.OUT_QKV:
             ns, tpb, ld_t, ld = o["n_split"], o["tok_per_batch"], o["ld_t"], o["ldo"]
             a = v[:, :ns]

@@ -103,7 +103,7 @@ def test_prep_modes(mode):
 
 
 def _gemm_case(P: Planner, g, *, B, H, W, Cin, N, taps, OH=None, OW=None, sy=1, sx=1, up=0, bmod=0, act=_lib.ACT_NONE,
-               res=False, rowvec=False, alpha=1.0, accumulate=False, out_kind="f32", geglu=False, bias=True):
+               res=False, rowvec=False, alpha=1.0, accumulate=False, out_kind="f32", geglu=False, bias=True, dual=False):
     Hs, Ws = H >> up, W >> up
     Bsrc = bmod if bmod else B
     src = F32(P.raw(Bsrc * Hs * Ws * Cin * 4), Bsrc * Hs * Ws, Cin)
@@ -127,6 +127,10 @@ def _gemm_case(P: Planner, g, *, B, H, W, Cin, N, taps, OH=None, OW=None, sy=1, 
     if out_kind == "f32":
         o = P.f32(M, n_out); kw["out"] = o
         ios["out"] = ("f32", o.ref, (M, n_out)); ins["out"] = torch.randn(M, n_out, generator=g)   # for accumulate
+        if dual:
+            dp = P.planes(M, n_out); kw["also_planes"] = dp
+            P.gemm(a, w, **kw)
+            return ios, ins, ("dual", (o, dp))
         P.gemm(a, w, **kw)
         return ios, ins, ("f32", o)
     if out_kind == "planes":
@@ -153,6 +157,7 @@ GEMM_CASES = {
     "nchw_out": dict(B=2, H=16, W=8, Cin=32, N=8, taps=plan.TAPS_3x3, out_kind="nchw"),
     "deepK_splitk": dict(B=2, H=8, W=2, Cin=640, N=640, taps=plan.TAPS_3x3, res=True, rowvec=True),
     "nobias": dict(B=1, H=130, W=1, Cin=96, N=288, taps=((0, 0),), bias=False),
+    "dual_out": dict(B=1, H=300, W=1, Cin=128, N=256, taps=((0, 0),), res=True, dual=True),
 }
 
 
@@ -166,6 +171,10 @@ def test_gemm_vs_emulator(case, impl):
     if case == "deepK_splitk" and impl != "simt":
         assert pl.ops[-1]["splitk"] > 1
     em, prog = run_both(pl, ins)
+    if kind == "dual":
+        o, dp = o
+        assert rel_l2(read_gpu_planes(prog, dp), em.read_planes(dp.hi, dp.lo, dp.rows, dp.Cp)) < 2e-5
+        kind = "f32"
     if kind == "f32":
         want, got = em.f32(o.ref, o.rows * o.C).clone(), read_gpu_f32(prog, o.ref, o.rows * o.C)
     elif kind == "planes":
