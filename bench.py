@@ -307,6 +307,16 @@ def main():
     t_e2e = timed(e2e_step, a.steps)
     clk = clocks.stop() if rank == 0 else None
 
+    # phase breakdown of one more generation (outside the timed regions)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.manual_seed(7)
+    ev[0].record(); z = eng.generate_latent(cond_d, unc_d, ddim_steps=S, guidance=3.5, eta=1.0)
+    ev[1].record(); mel = eng.decode_first_stage(z)
+    ev[2].record(); eng.mel_spectrogram_to_waveform(mel)
+    ev[3].record(); torch.cuda.synchronize()
+    breakdown = dict(sampler_ms=ev[0].elapsed_time(ev[1]), vae_decode_ms=ev[1].elapsed_time(ev[2]),
+                     vocoder_ms=ev[2].elapsed_time(ev[3]), ms_per_ddim_step=ev[0].elapsed_time(ev[1]) / S)
+
     clips = world * B * a.steps
     value, e2e_value = clips / t_dev, clips / t_e2e
     h2d = sum(t.numel() * 4 for c in (cond_h, unc_h) for t in c["context_list"] + c["mask_list"]) + \
@@ -344,7 +354,7 @@ def main():
                             l2="no explicit flush: 1.39 GB of UNet weights are re-streamed every DDIM step (working set >> 126 MB L2)",
                             parallelism=f"dp{world} (independent batch shards, weights broadcast once over NCCL)"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=wave_host.numel() * 4),
-                gpu_launches=launches, clocks=clk, roofline=roof, cpu_baseline=cpu, impl="native")
+                gpu_launches=launches, clocks=clk, roofline=roof, cpu_baseline=cpu, impl="native", breakdown=breakdown)
     if tcb is not None:
         line["torch_cuda_baseline"] = tcb
     print(json.dumps(line))
