@@ -95,15 +95,22 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must become a CUDA error, never a hung GPU box.
+// Bounded wait: a protocol bug must become a CUDA error, never a hung GPU box.  The timer is only
+// consulted every 4096 failed probes (try_wait itself suspends the thread in hardware), so the
+// hot path is a bare try_wait loop.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) {   // 4 s
-      printf("aldm: mbarrier wait timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-      __trap();
+    if ((++spins & 4095u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {   // 4 s
+        printf("aldm: mbarrier wait timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }

@@ -161,26 +161,49 @@ __device__ __forceinline__ bool epi_coalescable(const aldm_gemm_desc& d, int n_o
   return d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_PLANES || d.out_mode == ALDM_OUT_QKV;
 }
 
-__device__ __forceinline__ void epi_finish_coalesced(const aldm_gemm_desc& d, const RowInfo& r, int n0, const float* v,
-                                                     int n_out, float* stg, int lane) {
+// Per-tile row bookkeeping of the coalesced path: lane (rs = lane>>3, c4 = (lane&7)*4) handles rows
+// it*4+rs, it = 0..7; orow[it] / valid bits are fetched once per tile from the row-owner lanes.
+struct CoRows {
+  long long orow[8];
+  unsigned vmask;
+};
+
+__device__ __forceinline__ CoRows co_rows(const RowInfo& r, int lane) {
+  CoRows cr;
+  cr.vmask = __ballot_sync(0xffffffffu, r.valid);
+  const int rs = lane >> 3;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) cr.orow[it] = __shfl_sync(0xffffffffu, r.orow, it * 4 + rs);
+  return cr;
+}
+
+// issue the residual loads of one 32-column chunk (they are consumed after the TMEM read + transpose,
+// and the next chunk's loads are issued before the current chunk is processed: latency hidden)
+__device__ __forceinline__ void co_load_res(const aldm_gemm_desc& d, const CoRows& cr, int n0, int n_out, int lane, float4 (&rv)[8]) {
+  const int rs = lane >> 3, n = n0 + (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const bool ok = ((cr.vmask >> (it * 4 + rs)) & 1u) && n < n_out;
+    rv[it] = ok ? __ldg(reinterpret_cast<const float4*>(d.res + cr.orow[it] * d.ld_res + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void epi_finish_coalesced(const aldm_gemm_desc& d, const CoRows& cr, int n0, const float* v,
+                                                     int n_out, float* stg, int lane, const float4 (&rv)[8], bool has_rv) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
   __syncwarp();
-  const unsigned vmask = __ballot_sync(0xffffffffu, r.valid);
   const int rs = lane >> 3, c4 = (lane & 7) * 4;
   const int n = n0 + c4;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + rs;
-    const long long orow = __shfl_sync(0xffffffffu, r.orow, rr);
-    if (!((vmask >> rr) & 1u) || n >= n_out) continue;
+    if (!((cr.vmask >> rr) & 1u) || n >= n_out) continue;
+    const long long orow = cr.orow[it];
     float x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = stg[rr * 33 + c4 + i];
-    if (d.res) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(d.res + orow * d.ld_res + n));
-      x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
-    }
+    if (has_rv) { x[0] += rv[it].x; x[1] += rv[it].y; x[2] += rv[it].z; x[3] += rv[it].w; }
     if (d.alpha != 1.0f) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) x[i] *= d.alpha;
@@ -428,6 +451,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   const int M = d.B * d.OH * d.OW;
   const int nkb_total = d.Kpad / C::BK;
   const int total = tiles_m * tiles_n * d.splitk;
+  const int dbg = d.impl >> 8;     // profiling aids (scripts/prof_ops.py --dbg): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -506,8 +530,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           long long off = 0;
           if (ok) off = ((long long)(pb[i] + (ih >> d.up)) * Ws + (iw >> d.up)) * d.Cp + c;
           const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
-          cp_async_16(dst, ahi + off, ok ? 16u : 0u);
-          cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+          if (!(dbg & 1)) {
+            cp_async_16(dst, ahi + off, ok ? 16u : 0u);
+            cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+          }
         }
         cp_async_mbar_arrive_noinc(full_bar(s));
       }
@@ -523,6 +549,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
           mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+          if (dbg & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
           bulk_g2s(base + s * C::STAGE_BYTES + 2 * C::A_BYTES, wsrc + (long long)it * (2 * C::B_BYTES), 2 * C::B_BYTES,
                    full_bar(s));
@@ -552,12 +579,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);
           const uint64_t db_hi = umma_desc_sw128(sa + 2 * C::A_BYTES);
           const uint64_t db_lo = umma_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
+          if (!(dbg & 4)) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t o = (uint64_t)(ks * 2);
-            umma_bf16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
-            umma_bf16(tacc, da_hi + o, db_lo + o, idesc, 1);
-            umma_bf16(tacc, da_hi + o, db_hi + o, idesc, 1);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t o = (uint64_t)(ks * 2);
+              umma_bf16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
+              umma_bf16(tacc, da_hi + o, db_lo + o, idesc, 1);
+              umma_bf16(tacc, da_hi + o, db_hi + o, idesc, 1);
+            }
           }
           umma_commit(empty_bar(s));
         }
@@ -580,6 +609,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       const int m = mt * C::BM + trow_in_tile;
       const RowInfo r = decode_row(d, m, M);
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(lb * 32) << 16);
+      if (dbg & 8) {
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        continue;
+      }
       if (d.splitk > 1) {
         // raw partial sums -> ws[z][m][n], coalesced through the staging tile
         const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
@@ -603,8 +637,15 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       } else if (d.act == ALDM_ACT_GEGLU) {
         const int n_out = d.N / 2;
         const bool co = epi_coalescable(d, n_out);
+        const CoRows cr = co_rows(r, lane);
+        const bool pre = co && d.res != nullptr;
+        float4 rvA[8], rvB[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rvA[i] = make_float4(0.f, 0.f, 0.f, 0.f); rvB[i] = rvA[i]; }
+        if (pre) co_load_res(d, cr, nt * (BN / 2), n_out, lane, rvA);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          if (pre && c0 + 32 < BN / 2) co_load_res(d, cr, nt * (BN / 2) + c0 + 32, n_out, lane, rvB);
           uint32_t vr[32], gr[32];
           tmem_ld32(trow + c0, vr);
           tmem_ld32(trow + BN / 2 + c0, gr);
@@ -612,21 +653,32 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           float* v = reinterpret_cast<float*>(vr);
           float* g = reinterpret_cast<float*>(gr);
           epi_activate(d, r, nt * BN + c0, v, g);
-          if (co) epi_finish_coalesced(d, r, nt * (BN / 2) + c0, v, n_out, stg, lane);
+          if (co) epi_finish_coalesced(d, cr, nt * (BN / 2) + c0, v, n_out, stg, lane, rvA, pre);
           else epi_finish(d, r, nt * (BN / 2) + c0, 32, v, n_out);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rvA[i] = rvB[i];
         }
       } else {
         const bool co = epi_coalescable(d, d.N);
+        const CoRows cr = co_rows(r, lane);
+        const bool pre = co && d.res != nullptr;
+        float4 rvA[8], rvB[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rvA[i] = make_float4(0.f, 0.f, 0.f, 0.f); rvB[i] = rvA[i]; }
+        if (pre) co_load_res(d, cr, nt * BN, d.N, lane, rvA);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int n0 = nt * BN + c0;
+          if (pre && c0 + 32 < BN) co_load_res(d, cr, n0 + 32, d.N, lane, rvB);
           uint32_t vr[32];
           tmem_ld32(trow + c0, vr);
           tmem_ld_wait();
           float* v = reinterpret_cast<float*>(vr);
-          const int n0 = nt * BN + c0;
           epi_activate(d, r, n0, v, nullptr);
-          if (co && !(d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split)) epi_finish_coalesced(d, r, n0, v, d.N, stg, lane);
+          if (co && !(d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split)) epi_finish_coalesced(d, cr, n0, v, d.N, stg, lane, rvA, pre);
           else epi_finish(d, r, n0, 32, v, d.N);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rvA[i] = rvB[i];
         }
       }
       tc_fence_before();
@@ -792,7 +844,7 @@ static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   return ALDM_OK;
 }
 
-int gemm_num_launches(const aldm_gemm_desc& d) { return (d.impl != ALDM_GEMM_SIMT && d.splitk > 1) ? 2 : 1; }
+int gemm_num_launches(const aldm_gemm_desc& d) { return ((d.impl & 0xff) != ALDM_GEMM_SIMT && d.splitk > 1) ? 2 : 1; }
 
 int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
   const long long Mll = (long long)d.B * d.OH * d.OW;
@@ -825,7 +877,7 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
     ALDM_REQUIRE(d.out_hi && d.out_lo, ALDM_E_ARG, "gemm: null out planes");
     ALDM_REQUIRE(!d.accumulate, ALDM_E_UNSUPPORTED, "gemm: accumulate into planes");
   }
-  if (d.impl == ALDM_GEMM_SIMT) {
+  if ((d.impl & 0xff) == ALDM_GEMM_SIMT) {
     ALDM_REQUIRE(d.w_plain, ALDM_E_ARG, "gemm: SIMT path needs w_plain");
     const int Npad = cdiv(d.N, d.bn) * d.bn;
     const bool geglu = d.act == ALDM_ACT_GEGLU;
@@ -836,7 +888,7 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
     return ALDM_OK;
   }
   ALDM_REQUIRE(d.w_packed && aligned16(d.w_packed), ALDM_E_ARG, "gemm: w_packed null/unaligned");
-  if (d.impl == ALDM_GEMM_TC_V1) {
+  if ((d.impl & 0xff) == ALDM_GEMM_TC_V1) {
     switch (d.bn) {
       case 128: return launch_tc<128>(d, M, st);
       case 64: return launch_tc<64>(d, M, st);

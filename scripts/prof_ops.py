@@ -95,6 +95,7 @@ def main():
     ap.add_argument("--reps", type=int, default=40)
     ap.add_argument("--only", default=None)
     ap.add_argument("--impl", default="tc")
+    ap.add_argument("--dbg", type=int, default=0, help="GEMM profiling aid bits: 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     print(f"{'case':28s} {'us/launch':>10s} {'TFLOP/s':>9s}")
@@ -102,6 +103,12 @@ def main():
         if a.only and name not in a.only.split(","):
             continue
         pl, ins, first, flops = build(name, a.impl)
+        if a.dbg:
+            for o in pl.ops:
+                if o["kind"] == "gemm":
+                    o["impl"] = o["impl"] | (a.dbg << 8)
+        if first == 0:      # no setup op: insert a harmless copy so the range is not empty
+            pl.ops.insert(0, dict(kind="copy", src=plan.Ref("ws", 0), dst=plan.Ref("ws", 0), bytes=0)); first = 1
         prog = engine.DeviceProgram(pl, dev, dict(setup=(0, first), op=(first, len(pl.ops))))
         for k, v in ins.items():
             prog.view(k).copy_(v.to(dev))
