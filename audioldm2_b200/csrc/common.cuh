@@ -115,6 +115,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// non-blocking probe (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// pure spin variant for latency-critical single-thread waits
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) { printf("aldm: mbarrier spin timeout\n"); __trap(); }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) 16-byte with zero fill, completion signalled on an mbarrier
 // ------------------------------------------------------------------------------------------

@@ -451,7 +451,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   const int M = d.B * d.OH * d.OW;
   const int nkb_total = d.Kpad / C::BK;
   const int total = tiles_m * tiles_n * d.splitk;
-  const int dbg = d.impl >> 8;     // profiling aids (scripts/prof_ops.py --dbg): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue
+  const int dbg = d.impl >> 8;     // profiling aids (scripts/prof_ops.py --dbg): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue, 16 spin waits
+  auto WAIT = [&](uint32_t bar, uint32_t parity) {
+    if (dbg & 16) mbar_wait_spin(bar, parity); else WAIT(bar, parity);
+  };
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       }
       for (int it = 0; it < nkb; ++it, ++cnt) {
         const int s = cnt % C::STAGES;
-        mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+        WAIT(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
         const int k = (kb0 + it) * C::BK + j * 8;
         const bool kvalid = k < d.K;
         int tap = 0, c = 0;
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(d.w_packed) + ((long long)nt * nkb_total + kb0) * (2 * C::B_BYTES);
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
-          mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+          WAIT(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
           if (dbg & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
           bulk_g2s(base + s * C::STAGE_BYTES + 2 * C::A_BYTES, wsrc + (long long)it * (2 * C::B_BYTES), 2 * C::B_BYTES,
@@ -566,12 +569,12 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         int mt, nt, z, kb0, nkb;
         tile_coords(id, mt, nt, z, kb0, nkb);
         const uint32_t acc = tl & 1;
-        mbar_wait(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        WAIT(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * BN;
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
-          mbar_wait(full_bar(s), (cnt / C::STAGES) & 1);
+          WAIT(full_bar(s), (cnt / C::STAGES) & 1);
           tc_fence_after();
           fence_proxy_async();
           const uint32_t sa = base + s * C::STAGE_BYTES;
@@ -604,7 +607,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       int mt, nt, z, kb0, nkb;
       tile_coords(id, mt, nt, z, kb0, nkb);
       const uint32_t acc = tl & 1;
-      mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
+      WAIT(tfull_bar(acc), (tl >> 1) & 1);
       tc_fence_after();
       const int m = mt * C::BM + trow_in_tile;
       const RowInfo r = decode_row(d, m, M);
