@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   const int total = tiles_m * tiles_n * d.splitk;
   const int dbg = d.impl >> 8;     // profiling aids (scripts/prof_ops.py --dbg): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue, 16 spin waits
   auto WAIT = [&](uint32_t bar, uint32_t parity) {
-    if (dbg & 16) mbar_wait_spin(bar, parity); else WAIT(bar, parity);
+    if (dbg & 16) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
   };
 
   if (tid == 0) {
