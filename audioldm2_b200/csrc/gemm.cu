@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
           }
         }
-        cp_async_mbar_arrive_noinc(full_bar(s));
+        if (dbg & 32) mbar_arrive(full_bar(s)); else cp_async_mbar_arrive_noinc(full_bar(s));
       }
     }
   } else if (warp == 4) {
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
               umma_bf16(tacc, da_hi + o, db_hi + o, idesc, 1);
             }
           }
-          umma_commit(empty_bar(s));
+          if (dbg & 64) mbar_arrive(empty_bar(s)); else umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(acc));
       }
