@@ -458,12 +458,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 128 + 1);
+      // One arrival per producer WARP (not per thread: 128 arrivals on one mbarrier word serialise in the
+      // shared-memory atomic unit and cost ~1 us per stage) + the B producer's expect_tx arrival.
+      mbar_init(full_bar(s), 4 + 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);        // tcgen05.commit after the tile's last k-block
-      mbar_init(tempty_bar(a), 128);     // epilogue threads
+      mbar_init(tempty_bar(a), 4);       // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -538,8 +540,24 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
           }
         }
-        if (dbg & 32) mbar_arrive(full_bar(s)); else cp_async_mbar_arrive_noinc(full_bar(s));
+        // cp.async groups lag the barrier by LAG = STAGES-1 stages: after issuing stage cnt, wait until the
+        // group of stage cnt-LAG has landed, make it visible to the async proxy, and let ONE lane arrive.
+        cp_async_commit();
+        if (cnt >= (uint32_t)(C::STAGES - 1)) {
+          cp_async_wait_group<C::STAGES - 1>();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar((cnt - (C::STAGES - 1)) % C::STAGES));
+        }
       }
+    }
+    {   // drain: signal the stages still in flight
+      cp_async_wait_all();
+      fence_proxy_async();
+      __syncwarp();
+      const uint32_t first = cnt >= (uint32_t)(C::STAGES - 1) ? cnt - (C::STAGES - 1) : 0u;
+      if (lane == 0)
+        for (uint32_t c = first; c < cnt; ++c) mbar_arrive(full_bar(c % C::STAGES));
     }
   } else if (warp == 4) {
     // ===================== B producer =====================
@@ -614,7 +632,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(lb * 32) << 16);
       if (dbg & 8) {
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
         continue;
       }
       if (d.splitk > 1) {
@@ -685,7 +704,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
 
