@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
 
   if (tid == 0) {
     // one arrival per WARP everywhere (per-thread arrivals on one mbarrier word serialise in the smem atomic unit)
-    mbar_init(q_full, 1);
-    mbar_init(kv_full0, 1); mbar_init(kv_full0 + 8, 1);
+    mbar_init(q_full, 32);
+    mbar_init(kv_full0, 32); mbar_init(kv_full0 + 8, 32);
     mbar_init(kv_empty0, 1); mbar_init(kv_empty0 + 8, 1);
     mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
     fence_barrier_init();
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       cp_async_16(dst + QA1, qh + off, ok ? 16u : 0u);
       if (c < 4) cp_async_16(dst + QA2, ql + off, ok ? 16u : 0u);
     }
-    // Q shares cp.async group 0 with the first K/V tile; groups lag the barrier by one tile.
+    cp_async_mbar_arrive_noinc(q_full);
     for (int it = 0; it < nt; ++it) {
       const int s = it & 1, k0 = it * KT;
       mbar_wait(kv_empty0 + 8 * s, ((it >> 1) & 1) ^ 1);
@@ -180,18 +180,8 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         const long long off = ok ? ((long long)(bkv * d.heads + h) * ATT_D + r) * d.ld_t + k0 + c * 8 : 0;
         cp_async_16(vb + p * (ATT_D * 128) + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), (p ? vl : vh) + off, ok ? 16u : 0u);
       }
-      cp_async_commit();
-      if (it >= 1) {                      // tile it-1 (and Q) has landed: publish it
-        cp_async_wait_group<1>();
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) { if (it == 1) mbar_arrive(q_full); mbar_arrive(kv_full0 + 8 * ((it - 1) & 1)); }
-      }
+      cp_async_mbar_arrive_noinc(kv_full0 + 8 * s);
     }
-    cp_async_wait_all();
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) { if (nt == 1) mbar_arrive(q_full); mbar_arrive(kv_full0 + 8 * ((nt - 1) & 1)); }
   } else {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
@@ -203,7 +193,6 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         const int s = it & 1;
         mbar_wait(kv_full0 + 8 * s, (it >> 1) & 1);
         tc_fence_after();
-        fence_proxy_async();
         const uint64_t dK = umma_desc_sw128(base + KB + s * (KT * 128));
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_S, dA1 + 2 * ks, dK + 2 * ks, idS, ks > 0);   // q_hi k_hi + q_hi k_lo
@@ -212,7 +201,6 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         umma_commit(s_full);
         mbar_wait(p_full, it & 1);
         tc_fence_after();
-        fence_proxy_async();
         const uint64_t dVh = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128));
         const uint64_t dVl = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128) + ATT_D * 128);
 #pragma unroll

@@ -458,9 +458,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      // One arrival per producer WARP (not per thread: 128 arrivals on one mbarrier word serialise in the
-      // shared-memory atomic unit and cost ~1 us per stage) + the B producer's expect_tx arrival.
-      mbar_init(full_bar(s), 4 + 1);
+      // 128 cp.async producers (cp.async.mbarrier.arrive: completion-triggered, the producers never block
+      // on their own loads) + the B producer's expect_tx arrival.
+      mbar_init(full_bar(s), 128 + 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -540,24 +540,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
           }
         }
-        // cp.async groups lag the barrier by LAG = STAGES-1 stages: after issuing stage cnt, wait until the
-        // group of stage cnt-LAG has landed, make it visible to the async proxy, and let ONE lane arrive.
-        cp_async_commit();
-        if (cnt >= (uint32_t)(C::STAGES - 1)) {
-          cp_async_wait_group<C::STAGES - 1>();
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_bar((cnt - (C::STAGES - 1)) % C::STAGES));
-        }
+        cp_async_mbar_arrive_noinc(full_bar(s));
       }
-    }
-    {   // drain: signal the stages still in flight
-      cp_async_wait_all();
-      fence_proxy_async();
-      __syncwarp();
-      const uint32_t first = cnt >= (uint32_t)(C::STAGES - 1) ? cnt - (C::STAGES - 1) : 0u;
-      if (lane == 0)
-        for (uint32_t c = first; c < cnt; ++c) mbar_arrive(full_bar(c % C::STAGES));
     }
   } else if (warp == 4) {
     // ===================== B producer =====================
@@ -594,7 +578,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           const int s = cnt % C::STAGES;
           WAIT(full_bar(s), (cnt / C::STAGES) & 1);
           tc_fence_after();
-          fence_proxy_async();
+          if (dbg & 32) fence_proxy_async();
           const uint32_t sa = base + s * C::STAGE_BYTES;
           const uint64_t da_hi = umma_desc_sw128(sa);
           const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);
