@@ -173,6 +173,7 @@ def lib() -> C.CDLL:
         "aldm_offsetof_gemm": (C.c_size_t, [i32]),
         "aldm_last_error": (C.c_char_p, []),
         "aldm_device_check": (i32, [i32]),
+        "aldm_debug_timeline": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the symbol is not exported
@@ -191,7 +192,7 @@ EXPORTED = ["aldm_gemm", "aldm_prep", "aldm_pack_b", "aldm_attention", "aldm_sof
             "aldm_posterior_sample", "aldm_stft_mel", "aldm_program_create", "aldm_program_run",
             "aldm_program_run_range", "aldm_program_capture", "aldm_program_replay",
             "aldm_program_num_launches", "aldm_program_destroy", "aldm_abi_version", "aldm_sizeof_op",
-            "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check"]
+            "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check", "aldm_debug_timeline"]
 
 
 def check(rc: int, what: str = ""):

@@ -423,6 +423,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   }
 }
 
+// Debug timeline (profiling aid, dbg bit 128): CTA 0 records clock64() at pipeline events.
+// layout: [role 0..3][iteration 0..255][phase 0..1]
+__device__ long long g_timeline[4 * 256 * 2];
+#define ALDM_TL(role, i, ph)                                                      \
+  do {                                                                            \
+    if ((dbg & 128) && blockIdx.x == 0 && (i) < 256) g_timeline[((role) * 256 + (i)) * 2 + (ph)] = clock64(); \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------
 // persistent variant (default): one CTA per SM loops over output tiles; 320 threads =
 //   warps 0-3 A producers | warp 4 B (TMA bulk) | warp 5 MMA | warps 6-9 epilogue.
@@ -522,6 +530,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       for (int it = 0; it < nkb; ++it, ++cnt) {
         const int s = cnt % C::STAGES;
         WAIT(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+        if (tid == 0) ALDM_TL(0, cnt, 0);
         const int k = (kb0 + it) * C::BK + j * 8;
         const bool kvalid = k < d.K;
         int tap = 0, c = 0;
@@ -541,6 +550,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           }
         }
         cp_async_mbar_arrive_noinc(full_bar(s));
+        if (tid == 0) ALDM_TL(0, cnt, 1);
       }
     }
   } else if (warp == 4) {
@@ -554,6 +564,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
           WAIT(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+          ALDM_TL(1, cnt, 0);
           if (dbg & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
           bulk_g2s(base + s * C::STAGE_BYTES + 2 * C::A_BYTES, wsrc + (long long)it * (2 * C::B_BYTES), 2 * C::B_BYTES,
@@ -577,6 +588,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
           WAIT(full_bar(s), (cnt / C::STAGES) & 1);
+          ALDM_TL(2, cnt, 0);
           tc_fence_after();
           if (dbg & 32) fence_proxy_async();
           const uint32_t sa = base + s * C::STAGE_BYTES;
@@ -594,6 +606,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             }
           }
           if (dbg & 64) mbar_arrive(empty_bar(s)); else umma_commit(empty_bar(s));
+          ALDM_TL(2, cnt, 1);
         }
         umma_commit(tfull_bar(acc));
       }
@@ -610,6 +623,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       tile_coords(id, mt, nt, z, kb0, nkb);
       const uint32_t acc = tl & 1;
       WAIT(tfull_bar(acc), (tl >> 1) & 1);
+      if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
       tc_fence_after();
       const int m = mt * C::BM + trow_in_tile;
       const RowInfo r = decode_row(d, m, M);
@@ -690,6 +704,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (warp == 6 && lane == 0) ALDM_TL(3, tl, 1);
     }
   }
 
@@ -910,6 +925,13 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
 }
 
 }  // namespace aldm
+
+extern "C" int aldm_debug_timeline(long long* host_out, int32_t n) {
+  using namespace aldm;
+  ALDM_REQUIRE(host_out && n > 0 && n <= 4 * 256 * 2, ALDM_E_ARG, "debug_timeline: bad arguments");
+  ALDM_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * n));
+  return ALDM_OK;
+}
 
 extern "C" int aldm_gemm(const aldm_gemm_desc* d, void* stream) {
   if (!d) { aldm::set_error("aldm_gemm: null desc"); return ALDM_E_ARG; }

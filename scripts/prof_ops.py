@@ -120,6 +120,19 @@ def main():
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / a.reps
         print(f"{name:28s} {us:10.1f} {flops / (us * 1e-6) / 1e12 if flops else 0:9.1f}", flush=True)
+        if a.dbg & 128:
+            import ctypes as C
+            buf = (C.c_longlong * (4 * 256 * 2))()
+            _lib.check(_lib.lib().aldm_debug_timeline(buf, 4 * 256 * 2), "timeline")
+            t = torch.tensor(list(buf), dtype=torch.int64).reshape(4, 256, 2)
+            t0 = int(t[t > 0].min())
+            print("  iter | prod: wait_done issued | B: wait_done | MMA: full_seen committed | (cycles since first event)")
+            for i in range(0, 40):
+                r = lambda x: (int(x) - t0) if int(x) > 0 else -1
+                print(f"  {i:4d} | {r(t[0, i, 0]):7d} {r(t[0, i, 1]):7d} | {r(t[1, i, 0]):7d} | {r(t[2, i, 0]):7d} {r(t[2, i, 1]):7d}")
+            print("  tile | epi: tfull_seen done")
+            for i in range(0, 4):
+                print(f"  {i:4d} | {r(t[3, i, 0]):7d} {r(t[3, i, 1]):7d}")
 
 
 if __name__ == "__main__":
