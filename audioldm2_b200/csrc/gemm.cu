@@ -432,16 +432,35 @@ __device__ long long g_timeline[4 * 256 * 2];
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-// persistent variant (default): one CTA per SM loops over output tiles; 320 threads =
-//   warps 0-3 A producers | warp 4 B (TMA bulk) | warp 5 MMA | warps 6-9 epilogue.
-// Two TMEM accumulators (2 x BN columns) let the epilogue of tile i drain while the producers and
-// the tensor core already work on tile i+1; barrier init / TMEM alloc are paid once per CTA.
-// Tile order: split-K slice fastest, then n-tile, then m-tile, so CTAs running concurrently share
-// the same activation rows in L2.
+// persistent variant (default): one CTA per SM loops over output tiles; 448 threads =
+//   warps 0-3 A producers | warp 4 B (TMA bulk) | warp 5 MMA | warps 6-13 epilogue (two per TMEM lane
+//   quarter, alternating 32-column chunks).
+// Two TMEM accumulators (2 x BN columns) let the epilogue of tile i drain while the producers and the
+// tensor core already work on tile i+1; barrier init / TMEM alloc are paid once per CTA.
+// What the measured timeline (profiles/r01_gemm_timeline.txt) showed and this version fixes:
+//   * each role runs ONE warp per SM sub-partition, so dependent-instruction latency is fully exposed:
+//     the producers' per-stage address arithmetic (an integer division and eight 64-bit index chains)
+//     took ~1450 cycles against 768 cycles of MMA work.  Row bases and per-row tap-validity masks are
+//     now computed once per tile; a stage costs one add + one bit test per row.
+//   * the epilogue took ~26k cycles per tile with four warps and a generic (all modes inlined, 200 KB
+//     of SASS) body.  EPI selects a specialised body at compile time (0: linear/conv with optional
+//     bias, row vector, residual, dual/QKV plane outputs; 1: GEGLU; 2: everything else), and eight
+//     warps share the drain.
+// Tile order: split-K slice fastest, then n-tile, then m-tile, so CTAs running concurrently share the
+// same activation rows in L2.
 // ------------------------------------------------------------------------------------------
+enum { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2 };
+
 template <int BN>
-__global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n) {
-  using C = TcCfg<BN>;
+struct Tc3Cfg : TcCfg<BN> {
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int STG_BYTES = 8 * 32 * 33 * 4;     // one 32x33 fp32 transpose tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * TcCfg<BN>::STAGE_BYTES + 1024 + 256 + STG_BYTES;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n) {
+  using C = Tc3Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -459,21 +478,16 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   const int M = d.B * d.OH * d.OW;
   const int nkb_total = d.Kpad / C::BK;
   const int total = tiles_m * tiles_n * d.splitk;
-  const int dbg = d.impl >> 8;     // profiling aids (scripts/prof_ops.py --dbg): 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue, 16 spin waits
-  auto WAIT = [&](uint32_t bar, uint32_t parity) {
-    if (dbg & 16) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
-  };
+  const int dbg = d.impl >> 8;     // profiling aids (scripts/prof_ops.py --dbg): 1 skip A, 2 skip B, 4 skip MMA, 8 skip epilogue, 128 timeline
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      // 128 cp.async producers (cp.async.mbarrier.arrive: completion-triggered, the producers never block
-      // on their own loads) + the B producer's expect_tx arrival.
-      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(full_bar(s), 128 + 1);   // 128 cp.async producers (completion-triggered arrivals) + B expect_tx
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);        // tcgen05.commit after the tile's last k-block
-      mbar_init(tempty_bar(a), 4);       // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), 8);       // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -497,15 +511,17 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 
   if (warp < 4) {
     // ===================== A producers =====================
-    const int j = tid & 7;
-    const int rbase = tid >> 3;
+    const int j = tid & 7;                 // 16-byte chunk (8 channels) inside the 64-wide K block
+    const int rbase = tid >> 3;            // rows rbase + 16*i
     const uint32_t swz = (uint32_t)((j ^ (rbase & 7)) << 4);
     const int Hs = d.H >> d.up, Ws = d.W >> d.up;
     const __nv_bfloat16* ahi = reinterpret_cast<const __nv_bfloat16*>(d.a_hi);
     const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(d.a_lo);
     uint32_t cnt = 0;
     int last_mt = -1;
-    int ih0[8], iw0[8], pb[8];
+    int rowoff[8];            // element offset of tap (0,0) / channel 0 of each row (valid rows only)
+    uint32_t tapmask[8];      // bit t set <=> tap t of this row is inside the input
+    int ih0[8], iw0[8], pbh[8];   // only used by the nearest-upsample (up = 1) slow path
     for (int id = blockIdx.x; id < total; id += gridDim.x) {
       int mt, nt, z, kb0, nkb;
       tile_coords(id, mt, nt, z, kb0, nkb);
@@ -514,43 +530,65 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int m = mt * C::BM + rbase + 16 * i;
+          uint32_t msk = 0;
+          int off = 0;
+          ih0[i] = 0; iw0[i] = 0; pbh[i] = -1;
           if (m < M) {
             const int ow = m % d.OW;
             const int t = m / d.OW;
             const int oh = t % d.OH;
             const int b = t / d.OH;
-            ih0[i] = oh * d.sy;
-            iw0[i] = ow * d.sx;
-            pb[i] = (d.bmod > 0 ? b % d.bmod : b) * Hs;
-          } else {
-            ih0[i] = 0; iw0[i] = 0; pb[i] = -1;
+            const int y0 = oh * d.sy, x0 = ow * d.sx;
+            const int pb = (d.bmod > 0 ? b % d.bmod : b) * Hs;
+            ih0[i] = y0; iw0[i] = x0; pbh[i] = pb;
+            for (int tp = 0; tp < d.ntaps; ++tp) {
+              const int ih = y0 + d.dy[tp], iw = x0 + d.dx[tp];
+              if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) msk |= 1u << tp;
+            }
+            off = ((pb + y0) * Ws + x0) * d.Cp;
           }
+          tapmask[i] = msk;
+          rowoff[i] = off;
         }
       }
+      // (tap, c) of this thread's 8-channel chunk at the first k-block of the tile, then advanced by 64 per block
+      int k = kb0 * C::BK + j * 8;
+      int tap = k / d.Cp, c = k - tap * d.Cp;
       for (int it = 0; it < nkb; ++it, ++cnt) {
         const int s = cnt % C::STAGES;
-        WAIT(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+        mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
         if (tid == 0) ALDM_TL(0, cnt, 0);
-        const int k = (kb0 + it) * C::BK + j * 8;
-        const bool kvalid = k < d.K;
-        int tap = 0, c = 0;
-        if (kvalid) { tap = k / d.Cp; c = k - tap * d.Cp; }
-        const int dy = d.dy[tap], dx = d.dx[tap];
+        const bool kvalid = tap < d.ntaps;
+        const int tp = kvalid ? tap : 0;
         const uint32_t sa = base + s * C::STAGE_BYTES + swz;
+        if (d.up == 0) {
+          const int tapoff = (d.dy[tp] * Ws + d.dx[tp]) * d.Cp + c;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ih = ih0[i] + dy, iw = iw0[i] + dx;
-          const bool ok = kvalid && pb[i] >= 0 && ih >= 0 && ih < d.H && iw >= 0 && iw < d.W;
-          long long off = 0;
-          if (ok) off = ((long long)(pb[i] + (ih >> d.up)) * Ws + (iw >> d.up)) * d.Cp + c;
-          const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
-          if (!(dbg & 1)) {
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = kvalid && ((tapmask[i] >> tp) & 1u);
+            const long long off = ok ? (long long)(rowoff[i] + tapoff) : 0ll;
+            const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
+            if (!(dbg & 1)) {
+              cp_async_16(dst, ahi + off, ok ? 16u : 0u);
+              cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+            }
+          }
+        } else {      // nearest x2 upsample folded into the gather: source pixel = (ih >> 1, iw >> 1)
+          const int dy = d.dy[tp], dx = d.dx[tp];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = kvalid && ((tapmask[i] >> tp) & 1u);
+            long long off = 0;
+            if (ok) off = ((long long)(pbh[i] + ((ih0[i] + dy) >> 1)) * Ws + ((iw0[i] + dx) >> 1)) * d.Cp + c;
+            const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
             cp_async_16(dst, ahi + off, ok ? 16u : 0u);
             cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
           }
         }
         cp_async_mbar_arrive_noinc(full_bar(s));
         if (tid == 0) ALDM_TL(0, cnt, 1);
+        c += C::BK;
+        while (c >= d.Cp) { c -= d.Cp; ++tap; }
       }
     }
   } else if (warp == 4) {
@@ -563,7 +601,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(d.w_packed) + ((long long)nt * nkb_total + kb0) * (2 * C::B_BYTES);
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
-          WAIT(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+          mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
           ALDM_TL(1, cnt, 0);
           if (dbg & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
@@ -582,15 +620,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         int mt, nt, z, kb0, nkb;
         tile_coords(id, mt, nt, z, kb0, nkb);
         const uint32_t acc = tl & 1;
-        WAIT(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        mbar_wait(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * BN;
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
-          WAIT(full_bar(s), (cnt / C::STAGES) & 1);
+          mbar_wait(full_bar(s), (cnt / C::STAGES) & 1);
           ALDM_TL(2, cnt, 0);
           tc_fence_after();
-          if (dbg & 32) fence_proxy_async();
           const uint32_t sa = base + s * C::STAGE_BYTES;
           const uint64_t da_hi = umma_desc_sw128(sa);
           const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);
@@ -598,14 +635,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           const uint64_t db_lo = umma_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
           if (!(dbg & 4)) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < 4; ++ks) {            // 4 x K=16 (32 bytes) inside the 128B swizzle row
               const uint64_t o = (uint64_t)(ks * 2);
               umma_bf16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
               umma_bf16(tacc, da_hi + o, db_lo + o, idesc, 1);
               umma_bf16(tacc, da_hi + o, db_hi + o, idesc, 1);
             }
           }
-          if (dbg & 64) mbar_arrive(empty_bar(s)); else umma_commit(empty_bar(s));
+          umma_commit(empty_bar(s));
           ALDM_TL(2, cnt, 1);
         }
         umma_commit(tfull_bar(acc));
@@ -613,33 +650,31 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 6-9; TMEM lane block = warp % 4) =====================
+    // ===================== epilogue: warps 6-13; TMEM lane quarter = warp % 4, chunk parity = (warp-6)/4 =====================
     const int lb = warp & 3;
+    const int half = (warp - 6) >> 2;
     const int trow_in_tile = lb * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)) + lb * (32 * 33);
+    float* stg = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)) + (warp - 6) * (32 * 33);
     uint32_t tl = 0;
     for (int id = blockIdx.x; id < total; id += gridDim.x, ++tl) {
       int mt, nt, z, kb0, nkb;
       tile_coords(id, mt, nt, z, kb0, nkb);
       const uint32_t acc = tl & 1;
-      WAIT(tfull_bar(acc), (tl >> 1) & 1);
-      if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
-      tc_fence_after();
       const int m = mt * C::BM + trow_in_tile;
       const RowInfo r = decode_row(d, m, M);
+      const CoRows cr = co_rows(r, lane);
+      mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
+      if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
+      tc_fence_after();
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(lb * 32) << 16);
       if (dbg & 8) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        continue;
-      }
-      if (d.splitk > 1) {
+        // skip
+      } else if (d.splitk > 1) {
         // raw partial sums -> ws[z][m][n], coalesced through the staging tile
         const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
         const int rs = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(trow + c0, v);
           tmem_ld_wait();
@@ -654,51 +689,83 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           }
           __syncwarp();
         }
-      } else if (d.act == ALDM_ACT_GEGLU) {
+      } else if (EPI == EPI_GEGLU) {
+        // tile columns [0,BN/2) values, [BN/2,BN) gates; output width N/2, always coalescable (checked on the host)
         const int n_out = d.N / 2;
-        const bool co = epi_coalescable(d, n_out);
-        const CoRows cr = co_rows(r, lane);
-        const bool pre = co && d.res != nullptr;
-        float4 rvA[8], rvB[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { rvA[i] = make_float4(0.f, 0.f, 0.f, 0.f); rvB[i] = rvA[i]; }
-        if (pre) co_load_res(d, cr, nt * (BN / 2), n_out, lane, rvA);
+        float4 rv[8];
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-          if (pre && c0 + 32 < BN / 2) co_load_res(d, cr, nt * (BN / 2) + c0 + 32, n_out, lane, rvB);
+        for (int c0 = half * 32; c0 < BN / 2; c0 += 64) {
+          const int n0 = nt * (BN / 2) + c0;
+          const bool pre = d.res != nullptr;
+          if (pre) co_load_res(d, cr, n0, n_out, lane, rv);
           uint32_t vr[32], gr[32];
           tmem_ld32(trow + c0, vr);
           tmem_ld32(trow + BN / 2 + c0, gr);
           tmem_ld_wait();
           float* v = reinterpret_cast<float*>(vr);
           float* g = reinterpret_cast<float*>(gr);
-          epi_activate(d, r, nt * BN + c0, v, g);
-          if (co) epi_finish_coalesced(d, cr, nt * (BN / 2) + c0, v, n_out, stg, lane, rvA, pre);
-          else epi_finish(d, r, nt * (BN / 2) + c0, 32, v, n_out);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rvA[i] = rvB[i];
+          if (d.bias) { add_vec32(v, d.bias + nt * BN + c0); add_vec32(g, d.bias + nt * BN + BN / 2 + c0); }
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) v[i] *= gelu_f(g[i]);
+          epi_finish_coalesced(d, cr, n0, v, n_out, stg, lane, rv, pre);
         }
-      } else {
-        const bool co = epi_coalescable(d, d.N);
-        const CoRows cr = co_rows(r, lane);
-        const bool pre = co && d.res != nullptr;
-        float4 rvA[8], rvB[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { rvA[i] = make_float4(0.f, 0.f, 0.f, 0.f); rvB[i] = rvA[i]; }
-        if (pre) co_load_res(d, cr, nt * BN, d.N, lane, rvA);
+      } else if (EPI == EPI_FAST) {
+        // no activation; fp32 / planes / dual / QKV outputs, all through the coalesced path (host-checked)
+        float4 rv[8];
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
           const int n0 = nt * BN + c0;
-          if (pre && c0 + 32 < BN) co_load_res(d, cr, n0 + 32, d.N, lane, rvB);
+          const bool vpart = d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split;
+          const bool pre = d.res != nullptr && !vpart;
+          if (pre) co_load_res(d, cr, n0, d.N, lane, rv);
           uint32_t vr[32];
           tmem_ld32(trow + c0, vr);
           tmem_ld_wait();
           float* v = reinterpret_cast<float*>(vr);
-          epi_activate(d, r, n0, v, nullptr);
-          if (co && !(d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split)) epi_finish_coalesced(d, cr, n0, v, d.N, stg, lane, rvA, pre);
-          else epi_finish(d, r, n0, 32, v, d.N);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rvA[i] = rvB[i];
+          if (d.bias) add_vec32(v, d.bias + n0);
+          if (d.rowvec) add_vec32(v, d.rowvec + (long long)r.b * d.ld_rowvec + n0);
+          if (!vpart) {
+            epi_finish_coalesced(d, cr, n0, v, d.N, stg, lane, rv, pre);
+          } else if (r.valid) {
+            // V projection: transposed planes, lane == token -> consecutive lanes write consecutive bf16
+            const int b = r.m / d.tok_per_batch, tok = r.m - b * d.tok_per_batch;
+            const long long tb = ((long long)b * (d.N - d.n_split) + (n0 - d.n_split)) * d.ld_t + tok;
+            __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out2_hi) + tb;
+            __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out2_lo) + tb;
+            const int cnt_ = min(32, d.N - n0);
+            const bool last = tok == d.tok_per_batch - 1;
+#pragma unroll 4
+            for (int i = 0; i < cnt_; ++i) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+              hp[(long long)i * d.ld_t] = h;
+              lp[(long long)i * d.ld_t] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+              if (last)
+                for (int t = 1; tok + t < d.ld_t; ++t) {
+                  hp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
+                  lp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
+                }
+            }
+          }
+        }
+      } else {
+        // generic: any activation / output mode, row-owner stores
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          if (d.act == ALDM_ACT_GEGLU) {
+            if (c0 >= BN / 2) break;
+            uint32_t vr[32], gr[32];
+            tmem_ld32(trow + c0, vr);
+            tmem_ld32(trow + BN / 2 + c0, gr);
+            tmem_ld_wait();
+            epi_activate(d, r, nt * BN + c0, reinterpret_cast<float*>(vr), reinterpret_cast<float*>(gr));
+            epi_finish(d, r, nt * (BN / 2) + c0, 32, reinterpret_cast<float*>(vr), d.N / 2);
+          } else {
+            uint32_t vr[32];
+            tmem_ld32(trow + c0, vr);
+            tmem_ld_wait();
+            epi_activate(d, r, nt * BN + c0, reinterpret_cast<float*>(vr), nullptr);
+            epi_finish(d, r, nt * BN + c0, 32, reinterpret_cast<float*>(vr), d.N);
+          }
         }
       }
       tc_fence_before();
@@ -838,12 +905,12 @@ static int launch_tc(const aldm_gemm_desc& d, int M, cudaStream_t st) {
 
 static int g_num_sms = 0;
 
-template <int BN>
-static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
-  using C = TcCfg<BN>;
+template <int BN, int EPI>
+static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
+  using C = Tc3Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM2_BYTES));
+    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   if (g_num_sms == 0) {
@@ -854,7 +921,7 @@ static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   const int tiles_m = cdiv(M, C::BM), tiles_n = cdiv(d.N, BN);
   const long long total = (long long)tiles_m * tiles_n * d.splitk;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  gemm_tc2_kernel<BN><<<grid, 320, C::SMEM2_BYTES, st>>>(d, tiles_m, tiles_n);
+  gemm_tc3_kernel<BN, EPI><<<grid, 448, C::SMEM_BYTES, st>>>(d, tiles_m, tiles_n);
   ALDM_CHECK_CUDA(cudaGetLastError());
   if (d.splitk > 1) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
@@ -864,6 +931,18 @@ static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
     ALDM_CHECK_CUDA(cudaGetLastError());
   }
   return ALDM_OK;
+}
+
+template <int BN>
+static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
+  // pick the specialised epilogue: the planner's dominant cases take the compact bodies
+  const bool geglu = d.act == ALDM_ACT_GEGLU;
+  const int n_out = geglu ? d.N / 2 : d.N;
+  const bool co = d.splitk == 1 && n_out % 4 == 0 && d.ldo % 4 == 0 && (!d.res || d.ld_res % 4 == 0) &&
+                  (d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_PLANES || d.out_mode == ALDM_OUT_QKV);
+  if (co && geglu && d.out_mode != ALDM_OUT_QKV && BN >= 64) return launch_tc3_epi<BN, EPI_GEGLU>(d, M, st);
+  if (co && d.act == ALDM_ACT_NONE) return launch_tc3_epi<BN, EPI_FAST>(d, M, st);
+  return launch_tc3_epi<BN, EPI_GENERIC>(d, M, st);
 }
 
 int gemm_num_launches(const aldm_gemm_desc& d) { return ((d.impl & 0xff) != ALDM_GEMM_SIMT && d.splitk > 1) ? 2 : 1; }
