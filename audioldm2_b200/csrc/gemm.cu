@@ -690,14 +690,15 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           __syncwarp();
         }
       } else if (EPI == EPI_GEGLU) {
-        // tile columns [0,BN/2) values, [BN/2,BN) gates; output width N/2, always coalescable (checked on the host)
+        // tile columns [0,BN/2) values, [BN/2,BN) gates; output width N/2, coalescable and without residual
+        // (both checked on the host; the residual-free body keeps v/g in registers under the 128-register cap)
         const int n_out = d.N / 2;
         float4 rv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN / 2; c0 += 64) {
           const int n0 = nt * (BN / 2) + c0;
-          const bool pre = d.res != nullptr;
-          if (pre) co_load_res(d, cr, n0, n_out, lane, rv);
           uint32_t vr[32], gr[32];
           tmem_ld32(trow + c0, vr);
           tmem_ld32(trow + BN / 2 + c0, gr);
@@ -705,9 +706,9 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           float* v = reinterpret_cast<float*>(vr);
           float* g = reinterpret_cast<float*>(gr);
           if (d.bias) { add_vec32(v, d.bias + nt * BN + c0); add_vec32(g, d.bias + nt * BN + BN / 2 + c0); }
-#pragma unroll 4
+#pragma unroll      // full unroll: v/g must stay in registers (a partial unroll indexes them dynamically -> local memory)
           for (int i = 0; i < 32; ++i) v[i] *= gelu_f(g[i]);
-          epi_finish_coalesced(d, cr, n0, v, n_out, stg, lane, rv, pre);
+          epi_finish_coalesced(d, cr, n0, v, n_out, stg, lane, rv, false);
         }
       } else if (EPI == EPI_FAST) {
         // no activation; fp32 / planes / dual / QKV outputs, all through the coalesced path (host-checked)
@@ -732,14 +733,17 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
             const long long tb = ((long long)b * (d.N - d.n_split) + (n0 - d.n_split)) * d.ld_t + tok;
             __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out2_hi) + tb;
             __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out2_lo) + tb;
-            const int cnt_ = min(32, d.N - n0);
             const bool last = tok == d.tok_per_batch - 1;
-#pragma unroll 4
-            for (int i = 0; i < cnt_; ++i) {
-              const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
-              hp[(long long)i * d.ld_t] = h;
-              lp[(long long)i * d.ld_t] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
-              if (last)
+#pragma unroll      // full unroll keeps v[] in registers
+            for (int i = 0; i < 32; ++i) {
+              if (n0 + i < d.N) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+                hp[(long long)i * d.ld_t] = h;
+                lp[(long long)i * d.ld_t] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+              }
+            }
+            if (last) {       // zero the padding keys [tok_per_batch, ld_t) (the attention kernel multiplies them by P = 0)
+              for (int i = 0; i < 32 && n0 + i < d.N; ++i)
                 for (int t = 1; tok + t < d.ld_t; ++t) {
                   hp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
                   lp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
@@ -940,7 +944,7 @@ static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   const int n_out = geglu ? d.N / 2 : d.N;
   const bool co = d.splitk == 1 && n_out % 4 == 0 && d.ldo % 4 == 0 && (!d.res || d.ld_res % 4 == 0) &&
                   (d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_PLANES || d.out_mode == ALDM_OUT_QKV);
-  if (co && geglu && d.out_mode != ALDM_OUT_QKV && BN >= 64) return launch_tc3_epi<BN, EPI_GEGLU>(d, M, st);
+  if (co && geglu && !d.res && d.out_mode != ALDM_OUT_QKV && BN >= 64) return launch_tc3_epi<BN, EPI_GEGLU>(d, M, st);
   if (co && d.act == ALDM_ACT_NONE) return launch_tc3_epi<BN, EPI_FAST>(d, M, st);
   return launch_tc3_epi<BN, EPI_GENERIC>(d, M, st);
 }
