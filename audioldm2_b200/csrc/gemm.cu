@@ -451,6 +451,30 @@ __device__ long long g_timeline[4 * 256 * 2];
 // ------------------------------------------------------------------------------------------
 enum { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2 };
 
+// Division by a launch-time constant as multiply + shift (n < 2^31, d < 2^31): q = (n * M) >> (32 + l),
+// M = floor(2^(32+l) / d) + 1, l = ceil(log2 d).  The persistent roles run one warp per scheduler, so a
+// hardware-emulated integer division (~100 dependent instructions) per row per tile stalls the pipeline.
+struct FastDiv {
+  unsigned long long M;
+  int sh;
+  int d;
+  __device__ __forceinline__ int div(int n) const {
+    return (int)(((unsigned long long)(unsigned)n * M) >> sh);   // n >= 0
+  }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * d; }
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  int l = 0;
+  while ((1ll << l) < d) ++l;
+  f.M = (unsigned long long)((((unsigned __int128)1) << (32 + l)) / (unsigned)d) + 1ull;
+  f.sh = 32 + l;
+  f.d = d;
+  if (d == 1) { f.M = 1ull << 32; f.sh = 32; }
+  return f;
+}
+struct Tc3Divs { FastDiv ow, oh, cp, tn, bmod; };
+
 template <int BN>
 struct Tc3Cfg : TcCfg<BN> {
   static constexpr int STAGES = (BN == 128) ? 3 : 4;
@@ -459,7 +483,8 @@ struct Tc3Cfg : TcCfg<BN> {
 };
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n) {
+__global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n,
+                                                           const __grid_constant__ Tc3Divs fd) {
   using C = Tc3Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -501,12 +526,15 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   auto tile_coords = [&](int id, int& mt, int& nt, int& z, int& kb0, int& nkb) {
-    z = id % d.splitk;
-    const int r = id / d.splitk;
-    nt = r % tiles_n;
-    mt = r / tiles_n;
-    kb0 = (int)(((long long)z * nkb_total) / d.splitk);
-    nkb = (int)(((long long)(z + 1) * nkb_total) / d.splitk) - kb0;
+    int r = id;
+    z = 0; kb0 = 0; nkb = nkb_total;
+    if (d.splitk > 1) {
+      z = id % d.splitk;
+      r = id / d.splitk;
+      kb0 = (int)(((long long)z * nkb_total) / d.splitk);
+      nkb = (int)(((long long)(z + 1) * nkb_total) / d.splitk) - kb0;
+    }
+    fd.tn.divmod(r, mt, nt);
   };
 
   if (warp < 4) {
@@ -534,12 +562,13 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           int off = 0;
           ih0[i] = 0; iw0[i] = 0; pbh[i] = -1;
           if (m < M) {
-            const int ow = m % d.OW;
-            const int t = m / d.OW;
-            const int oh = t % d.OH;
-            const int b = t / d.OH;
+            int t, ow, b, oh;
+            fd.ow.divmod(m, t, ow);
+            fd.oh.divmod(t, b, oh);
             const int y0 = oh * d.sy, x0 = ow * d.sx;
-            const int pb = (d.bmod > 0 ? b % d.bmod : b) * Hs;
+            int bs = b;
+            if (d.bmod > 0) { int q; fd.bmod.divmod(b, q, bs); }
+            const int pb = bs * Hs;
             ih0[i] = y0; iw0[i] = x0; pbh[i] = pb;
             for (int tp = 0; tp < d.ntaps; ++tp) {
               const int ih = y0 + d.dy[tp], iw = x0 + d.dx[tp];
@@ -552,8 +581,9 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         }
       }
       // (tap, c) of this thread's 8-channel chunk at the first k-block of the tile, then advanced by 64 per block
-      int k = kb0 * C::BK + j * 8;
-      int tap = k / d.Cp, c = k - tap * d.Cp;
+      const int k = kb0 * C::BK + j * 8;
+      int tap, c;
+      fd.cp.divmod(k, tap, c);
       for (int it = 0; it < nkb; ++it, ++cnt) {
         const int s = cnt % C::STAGES;
         mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
@@ -661,7 +691,15 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
       tile_coords(id, mt, nt, z, kb0, nkb);
       const uint32_t acc = tl & 1;
       const int m = mt * C::BM + trow_in_tile;
-      const RowInfo r = decode_row(d, m, M);
+      RowInfo r;
+      {
+        r.m = m; r.valid = m < M;
+        const int mm = r.valid ? m : 0;
+        int t;
+        fd.ow.divmod(mm, t, r.ow);
+        fd.oh.divmod(t, r.b, r.oh);
+        r.orow = ((long long)r.b * d.OHF + (long long)r.oh * d.osy + d.ooy) * d.OWF + r.ow;
+      }
       const CoRows cr = co_rows(r, lane);
       mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
       if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
@@ -925,7 +963,10 @@ static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   const int tiles_m = cdiv(M, C::BM), tiles_n = cdiv(d.N, BN);
   const long long total = (long long)tiles_m * tiles_n * d.splitk;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  gemm_tc3_kernel<BN, EPI><<<grid, 448, C::SMEM_BYTES, st>>>(d, tiles_m, tiles_n);
+  Tc3Divs fd;
+  fd.ow = make_fastdiv(d.OW); fd.oh = make_fastdiv(d.OH); fd.cp = make_fastdiv(d.Cp); fd.tn = make_fastdiv(tiles_n);
+  fd.bmod = make_fastdiv(d.bmod > 0 ? d.bmod : 1);
+  gemm_tc3_kernel<BN, EPI><<<grid, 448, C::SMEM_BYTES, st>>>(d, tiles_m, tiles_n, fd);
   ALDM_CHECK_CUDA(cudaGetLastError());
   if (d.splitk > 1) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
