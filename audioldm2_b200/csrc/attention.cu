@@ -27,6 +27,12 @@ static constexpr int ATT_D = 32;
 // ------------------------------------------------------------------------------------------------
 // tcgen05 flash attention
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 namespace atc {
 constexpr int QT = 128, KT = 64;
 constexpr int QA1 = 0;                         // [128][128B]  q_hi | q_hi
@@ -87,24 +93,39 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       tmem_ld32(tmem_S + trow, reinterpret_cast<uint32_t*>(s));
       tmem_ld32(tmem_S + trow + 32, reinterpret_cast<uint32_t*>(s + 32));
       tmem_ld_wait();
-      float tmax = -INFINITY;
+      float mnew, corr, psum = 0.f;
+      if (k0 + KT <= d.Nk && !mrow) {
+        // interior tile, no mask: max on the raw scores (sl2 > 0), one FFMA + one MUFU per element
+        float tmax = s[0];
 #pragma unroll
-      for (int j = 0; j < KT; ++j) {
-        const int key = k0 + j;
-        float v = s[j] * sl2;
-        if (key >= d.Nk) v = -INFINITY;                               // beyond the key range: excluded
-        else if (mrow && __ldg(mrow + key) != 1.0f) v = -FLT_MAX;     // masked_fill(-finfo.max), attention.py:356-360
-        s[j] = v;
-        tmax = fmaxf(tmax, v);
-      }
-      const float mnew = fmaxf(mrun, tmax);
-      const float corr = (mrun == -INFINITY) ? 0.f : exp2f(mrun - mnew);
-      float psum = 0.f;
+        for (int j = 1; j < KT; ++j) tmax = fmaxf(tmax, s[j]);
+        mnew = fmaxf(mrun, tmax * sl2);
+        corr = ex2_approx(mrun - mnew);                  // mrun = -inf on the first tile -> 0
 #pragma unroll
-      for (int j = 0; j < KT; ++j) {
-        const float p = (s[j] == -INFINITY) ? 0.f : exp2f(s[j] - mnew);
-        s[j] = p;
-        psum += p;
+        for (int j = 0; j < KT; ++j) {
+          const float p = ex2_approx(fmaf(s[j], sl2, -mnew));
+          s[j] = p;
+          psum += p;
+        }
+      } else {
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+          const int key = k0 + j;
+          float v = s[j] * sl2;
+          if (key >= d.Nk) v = -INFINITY;                               // beyond the key range: excluded
+          else if (mrow && __ldg(mrow + key) != 1.0f) v = -FLT_MAX;     // masked_fill(-finfo.max), attention.py:356-360
+          s[j] = v;
+          tmax = fmaxf(tmax, v);
+        }
+        mnew = fmaxf(mrun, tmax);
+        corr = (mrun == -INFINITY) ? 0.f : ex2_approx(mrun - mnew);
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+          const float p = (s[j] == -INFINITY) ? 0.f : ex2_approx(s[j] - mnew);
+          s[j] = p;
+          psum += p;
+        }
       }
       lrun = lrun * corr + psum;
       mrun = mnew;
@@ -163,22 +184,30 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       if (c < 4) cp_async_16(dst + QA2, ql + off, ok ? 16u : 0u);
     }
     cp_async_mbar_arrive_noinc(q_full);
+    // K/V tiles: every lane owns one 16-byte chunk column c and rows r0 + 4i; all row bases are hoisted out of
+    // the tile loop (the loader is a single warp: per-element 64-bit index arithmetic was the bottleneck)
+    const int c = lane & 7, r0 = lane >> 3;
+    const __nv_bfloat16* kcol = (c < 4 ? kh : kl) + (long long)bkv * d.Nk * d.ldk + d.k_col + h * ATT_D + (c & 3) * 8;
+    const long long vrow0 = ((long long)(bkv * d.heads + h) * ATT_D + r0) * d.ld_t + c * 8;
+    const long long kstep = 4ll * d.ldk, vstep = 4ll * d.ld_t;
     for (int it = 0; it < nt; ++it) {
       const int s = it & 1, k0 = it * KT;
       mbar_wait(kv_empty0 + 8 * s, ((it >> 1) & 1) ^ 1);
       const uint32_t kb = base + KB + s * (KT * 128);
-      for (int idx = lane; idx < KT * 8; idx += 32) {
-        const int r = idx >> 3, c = idx & 7;
+      const __nv_bfloat16* kp = kcol + (long long)(k0 + r0) * d.ldk;
+#pragma unroll
+      for (int i = 0; i < KT / 4; ++i) {
+        const int r = r0 + 4 * i;
         const bool ok = k0 + r < d.Nk;
-        const long long off = ok ? ((long long)bkv * d.Nk + k0 + r) * d.ldk + d.k_col + h * ATT_D + (c & 3) * 8 : 0;
-        cp_async_16(kb + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), (c < 4 ? kh : kl) + off, ok ? 16u : 0u);
+        cp_async_16(kb + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), ok ? kp + i * kstep : kcol, ok ? 16u : 0u);
       }
       const uint32_t vb = base + VT + s * (2 * ATT_D * 128);
-      for (int idx = lane; idx < 2 * ATT_D * 8; idx += 32) {
-        const int p = idx >> 8, r = (idx >> 3) & 31, c = idx & 7;        // plane, d row, 8-key chunk
-        const bool ok = k0 + c * 8 < d.Nk;
-        const long long off = ok ? ((long long)(bkv * d.heads + h) * ATT_D + r) * d.ld_t + k0 + c * 8 : 0;
-        cp_async_16(vb + p * (ATT_D * 128) + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), (p ? vl : vh) + off, ok ? 16u : 0u);
+      const bool vok = k0 + c * 8 < d.Nk;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int pl = i >> 3, r = r0 + 4 * (i & 7);
+        const __nv_bfloat16* vp = (pl ? vl : vh) + vrow0 + (i & 7) * vstep + k0;
+        cp_async_16(vb + pl * (ATT_D * 128) + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), vok ? vp : vh, vok ? 16u : 0u);
       }
       cp_async_mbar_arrive_noinc(kv_full0 + 8 * s);
     }

@@ -206,6 +206,81 @@ __global__ void ew_kernel(const __grid_constant__ aldm_prep_desc d) {
   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + row * d.Cp + c) = l;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GroupNorm fast path (channels per group multiple of 4, i.e. C multiple of 128): a thread owns one
+// 4-channel column and walks the rows of its block -> no per-element group bookkeeping, fully
+// coalesced float4 rows, one shared-memory reduction per thread at the end.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_stats_col_kernel(const __grid_constant__ aldm_prep_desc d, int nblk) {
+  __shared__ float s_sum[32], s_sq[32];
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int C = d.c0 + d.c1, Q = C >> 2, cpg = C / d.groups;
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int rows_per = (d.HW + nblk - 1) / nblk;
+  const int r0 = blk * rows_per, r1 = min(d.HW, r0 + rows_per);
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    float a = 0.f, a2 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float4 v = load_cat4(d, (long long)b * d.HW + r, q * 4);
+      a += (v.x + v.y) + (v.z + v.w);
+      a2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, a2))));
+    }
+    const int g = (q * 4) / cpg;
+    atomicAdd(&s_sum[g], a);
+    atomicAdd(&s_sq[g], a2);
+  }
+  __syncthreads();
+  if (threadIdx.x < d.groups) {
+    double* p = d.scratch + (((long long)b * nblk + blk) * d.groups + threadIdx.x) * 2;
+    p[0] = (double)s_sum[threadIdx.x];
+    p[1] = (double)s_sq[threadIdx.x];
+  }
+}
+
+__global__ void gn_apply_col_kernel(const __grid_constant__ aldm_prep_desc d, int nblk_stats) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.y;
+  const int C = d.c0 + d.c1, Q = C >> 2, cpg = C / d.groups;
+  if (threadIdx.x < d.groups) {
+    double s = 0.0, s2 = 0.0;
+    for (int k = 0; k < nblk_stats; ++k) {
+      const double* p = d.scratch + (((long long)b * nblk_stats + k) * d.groups + threadIdx.x) * 2;
+      s += p[0]; s2 += p[1];
+    }
+    const double n = (double)d.HW * cpg;
+    const double mean = s / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)d.eps));
+  }
+  __syncthreads();
+  const int rows_per = (d.HW + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per, r1 = min(d.HW, r0 + rows_per);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+  const bool act = d.mode == ALDM_PREP_GN_SILU;
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    const int g = (q * 4) / cpg;
+    const float4 ga = *reinterpret_cast<const float4*>(d.gamma + q * 4);
+    const float4 be = *reinterpret_cast<const float4*>(d.beta + q * 4);
+    const float rs = s_rstd[g], mu = s_mean[g];
+    const float sc[4] = {rs * ga.x, rs * ga.y, rs * ga.z, rs * ga.w};
+    const float sh[4] = {be.x - mu * sc[0], be.y - mu * sc[1], be.z - mu * sc[2], be.w - mu * sc[3]};
+    for (int r = r0; r < r1; ++r) {
+      const long long row = (long long)b * d.HW + r;
+      const float4 v = load_cat4(d, row, q * 4);
+      float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+      if (act) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) y[e] = silu_f(y[e]);
+      }
+      store_planes4(hi + row * d.Cp + q * 4, lo + row * d.Cp + q * 4, y);
+    }
+  }
+}
+
 int prep_num_launches(const aldm_prep_desc& d) {
   return (d.mode == ALDM_PREP_GN || d.mode == ALDM_PREP_GN_SILU) ? 2 : 1;
 }
@@ -222,14 +297,28 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
     ALDM_REQUIRE(C % 4 == 0 && d.c0 % 4 == 0 && d.Cp == C, ALDM_E_SHAPE, "prep GN: channels must be multiples of 4/8");
     ALDM_REQUIRE(d.rows == d.B * d.HW, ALDM_E_SHAPE, "prep GN: rows != B*HW");
     ALDM_REQUIRE(!d.src_nchw, ALDM_E_UNSUPPORTED, "prep GN: NCHW source");
-    int nblk = cdiv(d.HW, 32);
-    if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;
-    gn_stats_kernel<<<dim3(nblk, d.B), 256, 0, st>>>(d, nblk);
-    ALDM_CHECK_CUDA(cudaGetLastError());
-    int nap = cdiv(d.HW, 16);
-    if (nap > 128) nap = 128;
-    gn_apply_kernel<<<dim3(nap, d.B), 256, 0, st>>>(d, nblk);
-    ALDM_CHECK_CUDA(cudaGetLastError());
+    const int cpg = C / d.groups;
+    if (cpg % 4 == 0) {
+      // column-owner kernels: ~8 rows per block so that even the 64-pixel level fills the machine
+      int nblk = cdiv(d.HW, 8);
+      if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;
+      const int thr = (C / 4) >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
+      gn_stats_col_kernel<<<dim3(nblk, d.B), thr, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(cudaGetLastError());
+      int nap = cdiv(d.HW, 4);
+      if (nap > 256) nap = 256;
+      gn_apply_col_kernel<<<dim3(nap, d.B), thr, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(cudaGetLastError());
+    } else {
+      int nblk = cdiv(d.HW, 32);
+      if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;
+      gn_stats_kernel<<<dim3(nblk, d.B), 256, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(cudaGetLastError());
+      int nap = cdiv(d.HW, 16);
+      if (nap > 128) nap = 128;
+      gn_apply_kernel<<<dim3(nap, d.B), 256, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(cudaGetLastError());
+    }
   } else if (d.mode == ALDM_PREP_LN) {
     ALDM_REQUIRE(d.gamma && d.beta, ALDM_E_ARG, "prep LN: null gamma/beta");
     ALDM_REQUIRE(d.c1 == 0 && C % 4 == 0 && C <= 1024 && d.Cp == C, ALDM_E_UNSUPPORTED, "prep LN: C=%d", C);

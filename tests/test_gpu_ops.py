@@ -76,6 +76,22 @@ def test_masked_blend_matches_oracle():
     assert rel_l2(got, want) < 1e-6
 
 
+def test_groupnorm_fast_path():
+    """C multiple of 128 (4 | channels per group) takes the column-owner kernels; concat of two sources."""
+    g = torch.Generator().manual_seed(21)
+    P = Planner(keep_plain=True)
+    B, HW = 3, 70
+    a = F32(P.raw(B * HW * 256 * 4), B * HW, 256)
+    b = F32(P.raw(B * HW * 128 * 4), B * HW, 128)
+    gam = P.vec(1 + 0.1 * torch.randn(384, generator=g)); bet = P.vec(0.1 * torch.randn(384, generator=g))
+    o1 = P.prep(_lib.PREP_GN_SILU, a, b, gam, bet, eps=1e-5, B=B, HW=HW)
+    o2 = P.prep(_lib.PREP_GN, a, None, gam, bet, eps=1e-6, B=B, HW=HW)
+    pl = P.finish(dict(a=("f32", a.ref, (a.rows, a.C)), b=("f32", b.ref, (b.rows, b.C))))
+    em, prog = run_both(pl, dict(a=torch.randn(a.rows, a.C, generator=g) * 2 + 0.5, b=torch.randn(b.rows, b.C, generator=g)))
+    for o in (o1, o2):
+        assert rel_l2(read_gpu_planes(prog, o), em.read_planes(o.hi, o.lo, o.rows, o.Cp)) < 2e-5
+
+
 @pytest.mark.parametrize("mode", ["copy", "silu", "lrelu", "gn", "gn_silu", "ln", "nchw", "cat", "pad"])
 def test_prep_modes(mode):
     g = torch.Generator().manual_seed(2)
