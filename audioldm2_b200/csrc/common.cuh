@@ -57,8 +57,22 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// exact (erf) GELU as F.gelu default (attention.py:44)
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf GELU as F.gelu default (attention.py:44).  erf via Abramowitz-Stegun 7.1.26 (|err| < 5e-7 in fp32,
+// i.e. at fp32 round-off of the GELU output): 1 RCP + 1 EX2 + 8 FMA-class instructions instead of the
+// ~40-instruction erff -- the GEGLU epilogue is issue-bound (profiles/r01_gemm_timeline_tc3.txt).
+__device__ __forceinline__ float gelu_f(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;     // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
 
 // ------------------------------------------------------------------------------------------
 // shared-memory address + mbarrier

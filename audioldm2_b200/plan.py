@@ -244,13 +244,29 @@ class Planner:
     def vec(self, t: torch.Tensor) -> Ref:
         return Ref("w", self.arena.add(t.float().contiguous()))
 
+    def bn_for_rows(self, N: int, m_rows: Optional[int], geglu: bool = False) -> int:
+        """N tile: 128 unless the GEMM is too small to give every SM a tile -- then the widest tile that
+        yields >= ~0.8 * n_sm tiles (per-tile time of a short K loop is dominated by fixed latencies, so
+        more, narrower tiles in flight win)."""
+        cands = [b for b in ((128, 64) if geglu else (128, 64, 32)) if N % b == 0]
+        if not cands:
+            return 128 if geglu else packing.choose_bn(N)
+        if not m_rows:
+            return cands[0]
+        mt = math.ceil(m_rows / 128)
+        for b in cands:
+            if mt * (N // b) >= int(0.8 * self.n_sm):
+                return b
+        return cands[-1]
+
     def wmat(self, wm: torch.Tensor, bias: Optional[torch.Tensor], ntaps: int, cp: int, geglu: bool = False,
-             bn: Optional[int] = None) -> WMat:
+             bn: Optional[int] = None, m_rows: Optional[int] = None) -> WMat:
         N, K = wm.shape
         assert K == ntaps * cp
-        bn = bn or packing.choose_bn(N)
+        # narrow tiles only pay for short K loops; long-K (deep conv) GEMMs keep 128-wide tiles + split-K,
+        # which moves half the operand bytes
+        bn = bn or self.bn_for_rows(N, m_rows if K <= 2048 else None, geglu)
         if geglu:
-            bn = 128
             order = packing.geglu_row_order(N // 2, bn)
             wm = wm[order]
             bias = bias[order] if bias is not None else None
@@ -270,10 +286,10 @@ class Planner:
                 return b
         raise ValueError((N, n_split))
 
-    def conv_w(self, sd, name: str, scale: float = 1.0) -> WMat:
+    def conv_w(self, sd, name: str, scale: float = 1.0, m_rows: Optional[int] = None) -> WMat:
         w = sd[name + ".weight"].float() * scale
         wm, taps, cp = packing.conv_weight_matrix(w)
-        return self.wmat(wm, sd.get(name + ".bias"), taps, cp)
+        return self.wmat(wm, sd.get(name + ".bias"), taps, cp, m_rows=m_rows)
 
     # ---- workspace -----------------------------------------------------------------------
     def f32(self, rows: int, Cc: int) -> F32:
@@ -502,7 +518,7 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
         p1 = P.prep(_lib.PREP_GN_SILU, x, x2, P.vec(sd[n + ".in_layers.0.weight"]), P.vec(sd[n + ".in_layers.0.bias"]),
                     eps=1e-5, B=Bt, HW=H * W)
         h1 = P.f32(rows, l.cout)
-        P.gemm(p1, P.conv_w(sd, n + ".in_layers.2"), B=Bt, H=H, W=W, taps=TAPS_3x3, out=h1,
+        P.gemm(p1, P.conv_w(sd, n + ".in_layers.2", m_rows=rows), B=Bt, H=H, W=W, taps=TAPS_3x3, out=h1,
                rowvec=emb_all.ref + emb_off[n] * 4, ld_rowvec=emb_total)
         P.free(p1)
         p2 = P.prep(_lib.PREP_GN_SILU, h1, None, P.vec(sd[n + ".out_layers.0.weight"]), P.vec(sd[n + ".out_layers.0.bias"]),
@@ -512,14 +528,14 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
         if l.cin != l.cout:
             px = P.prep(_lib.PREP_COPY, x, x2)
             skip = P.f32(rows, l.cout)
-            P.gemm(px, P.conv_w(sd, n + ".skip_connection"), B=Bt, H=H, W=W, out=skip)
+            P.gemm(px, P.conv_w(sd, n + ".skip_connection", m_rows=rows), B=Bt, H=H, W=W, out=skip)
             P.free(px)
             res = skip
         else:
             assert x2 is None
             res = x
         out = P.f32(rows, l.cout)
-        P.gemm(p2, P.conv_w(sd, n + ".out_layers.3"), B=Bt, H=H, W=W, taps=TAPS_3x3, out=out, res=res)
+        P.gemm(p2, P.conv_w(sd, n + ".out_layers.3", m_rows=rows), B=Bt, H=H, W=W, taps=TAPS_3x3, out=out, res=res)
         P.free(p2, skip)
         return out
 
@@ -541,12 +557,12 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
         else:
             kpl, vtp, L = kv
             q = P.planes(h.rows, Cc)
-            P.gemm(p, P.conv_w(sd, nm + ".to_q"), B=1, H=h.rows, out_planes=q)
+            P.gemm(p, P.conv_w(sd, nm + ".to_q", m_rows=h.rows), B=1, H=h.rows, out_planes=q)
             P.free(p)
             P.attn(q, 0, kpl, 0, vtp, ao, B=Bt, heads=heads, Nq=HW, Nk=L, mask=mask, scale=scale)
             P.free(q)
         out = P.f32(h.rows, Cc)
-        P.gemm(ao, P.conv_w(sd, nm + ".to_out.0"), B=1, H=h.rows, out=out, res=h)
+        P.gemm(ao, P.conv_w(sd, nm + ".to_out.0", m_rows=h.rows), B=1, H=h.rows, out=out, res=h)
         P.free(ao)
         return out
 
@@ -555,7 +571,7 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
         n, Cc, HW = l.name, l.cin, H * W
         p = P.prep(_lib.PREP_GN, x, None, P.vec(sd[n + ".norm.weight"]), P.vec(sd[n + ".norm.bias"]), eps=1e-6, B=Bt, HW=HW)
         h = P.f32(x.rows, Cc)
-        P.gemm(p, P.conv_w(sd, n + ".proj_in"), B=Bt, H=H, W=W, out=h)
+        P.gemm(p, P.conv_w(sd, n + ".proj_in", m_rows=x.rows), B=Bt, H=H, W=W, out=h)
         P.free(p)
         for d in range(l.depth):
             b = f"{n}.transformer_blocks.{d}"
@@ -567,17 +583,17 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
             wff = sd[b + ".ff.net.0.proj.weight"].float()
             wm, taps, cp = packing.conv_weight_matrix(wff)
             g = P.planes(h.rows, 4 * Cc)
-            P.gemm(p, P.wmat(wm, sd[b + ".ff.net.0.proj.bias"], taps, cp, geglu=True), B=1, H=h.rows, out_planes=g,
+            P.gemm(p, P.wmat(wm, sd[b + ".ff.net.0.proj.bias"], taps, cp, geglu=True, m_rows=h.rows), B=1, H=h.rows, out_planes=g,
                    act=_lib.ACT_GEGLU)
             P.free(p)
             h2 = P.f32(h.rows, Cc)
             last = d == l.depth - 1
             hp = P.planes(h.rows, Cc) if last else None      # proj_out's operand, written by the same epilogue
-            P.gemm(g, P.conv_w(sd, b + ".ff.net.2"), B=1, H=h.rows, out=h2, res=h, also_planes=hp)
+            P.gemm(g, P.conv_w(sd, b + ".ff.net.2", m_rows=h.rows), B=1, H=h.rows, out=h2, res=h, also_planes=hp)
             P.free(g, h); h = h2
         p = hp; P.free(h)
         out = P.f32(x.rows, Cc)
-        P.gemm(p, P.conv_w(sd, n + ".proj_out"), B=Bt, H=H, W=W, out=out, res=x)
+        P.gemm(p, P.conv_w(sd, n + ".proj_out", m_rows=x.rows), B=Bt, H=H, W=W, out=out, res=x)
         P.free(p)
         return out
 
