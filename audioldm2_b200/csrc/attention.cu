@@ -42,7 +42,7 @@ constexpr int VT = KB + 2 * KT * 128;          // 2 x {hi,lo} x [32][128B]
 constexpr int PP = VT + 2 * 2 * ATT_D * 128;   // {hi,lo} x [128][128B]
 constexpr int BAR = PP + 2 * QT * 128;
 constexpr int SMEM = BAR + 128 + 1024;
-constexpr int TMEM_COLS = 128;                 // S: cols [0,64), O_tile: cols [64,96)
+constexpr int TMEM_COLS = 256;                 // S double buffer: cols [0,64) / [64,128); O_tile: cols [128,160)
 }  // namespace atc
 
 __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_constant__ aldm_attn_desc d) {
@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   const uint32_t bar = base + BAR;
-  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 24, s_full = bar + 40, p_full = bar + 48,
-                 o_full = bar + 56, tmem_slot = bar + 64;
+  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 24, s_full0 = bar + 40, p_full = bar + 56,
+                 o_full = bar + 64, tmem_slot = bar + 72;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
   const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
@@ -64,15 +64,15 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
     mbar_init(q_full, 32);
     mbar_init(kv_full0, 32); mbar_init(kv_full0 + 8, 32);
     mbar_init(kv_empty0, 1); mbar_init(kv_empty0 + 8, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    mbar_init(s_full0, 1); mbar_init(s_full0 + 8, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 5) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + BAR + 64);
-  const uint32_t tmem_S = tmem, tmem_O = tmem + 64;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + BAR + 72);
+  const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
 
   if (warp < 4) {
     // =============================== softmax + output ===============================
@@ -87,11 +87,11 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
     const float* mrow = d.mask ? d.mask + (long long)bkv * d.Nk : nullptr;
     for (int it = 0; it < nt; ++it) {
       const int k0 = it * KT;
-      mbar_wait(s_full, it & 1);
+      mbar_wait(s_full0 + 8 * (it & 1), (it >> 1) & 1);
       tc_fence_after();
       float s[KT];
-      tmem_ld32(tmem_S + trow, reinterpret_cast<uint32_t*>(s));
-      tmem_ld32(tmem_S + trow + 32, reinterpret_cast<uint32_t*>(s + 32));
+      tmem_ld32(tmem_S + (it & 1) * KT + trow, reinterpret_cast<uint32_t*>(s));
+      tmem_ld32(tmem_S + (it & 1) * KT + trow + 32, reinterpret_cast<uint32_t*>(s + 32));
       tmem_ld_wait();
       float mnew, corr, psum = 0.f;
       if (k0 + KT <= d.Nk && !mrow) {
@@ -129,6 +129,18 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       }
       lrun = lrun * corr + psum;
       mrun = mnew;
+      // Deferred accumulation: fold in O_tile of the PREVIOUS key tile (its P V product has long finished
+      // while this tile's probabilities were computed), then rescale to the new running maximum.  Waiting
+      // for o_full(it-1) here also guarantees the tensor core is done reading the P buffer we overwrite next.
+      if (it > 0) {
+        mbar_wait(o_full, (it - 1) & 1);
+        tc_fence_after();
+        float ot[ATT_D];
+        tmem_ld32(tmem_O + trow, reinterpret_cast<uint32_t*>(ot));
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < ATT_D; ++i) o[i] = (o[i] + ot[i]) * corr;
+      }
       uint8_t* ph = sm + PP + row * 128;
 #pragma unroll
       for (int c = 0; c < KT / 8; ++c) {
@@ -142,13 +154,15 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      mbar_wait(o_full, it & 1);
+    }
+    {
+      mbar_wait(o_full, (nt - 1) & 1);
       tc_fence_after();
       float ot[ATT_D];
       tmem_ld32(tmem_O + trow, reinterpret_cast<uint32_t*>(ot));
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < ATT_D; ++i) o[i] = fmaf(o[i], corr, ot[i]);
+      for (int i = 0; i < ATT_D; ++i) o[i] += ot[i];
     }
     tc_fence_before();
     if (q < d.Nq) {
@@ -217,17 +231,27 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       constexpr uint32_t idS = umma_idesc_bf16(128, KT), idO = umma_idesc_bf16(128, ATT_D);
       const uint64_t dA1 = umma_desc_sw128(base + QA1), dA2 = umma_desc_sw128(base + QA2);
       const uint64_t dPh = umma_desc_sw128(base + PP), dPl = umma_desc_sw128(base + PP + QT * 128);
+      auto issue_S = [&](int t) {      // S(t) = Q K(t)^T into TMEM buffer t & 1
+        const int st = t & 1;
+        mbar_wait(kv_full0 + 8 * st, (t >> 1) & 1);      // returns at once when the caller has already seen it complete
+        tc_fence_after();
+        const uint64_t dK = umma_desc_sw128(base + KB + st * (KT * 128));
+        const uint32_t tS = tmem_S + st * KT;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_bf16(tS, dA1 + 2 * ks, dK + 2 * ks, idS, ks > 0);   // q_hi k_hi + q_hi k_lo
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dA2 + 2 * ks, dK + 2 * ks, idS, 1);        // q_lo k_hi
+        umma_commit(s_full0 + 8 * st);
+      };
       mbar_wait(q_full, 0);
+      issue_S(0);
       for (int it = 0; it < nt; ++it) {
         const int s = it & 1;
-        mbar_wait(kv_full0 + 8 * s, (it >> 1) & 1);
-        tc_fence_after();
-        const uint64_t dK = umma_desc_sw128(base + KB + s * (KT * 128));
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_S, dA1 + 2 * ks, dK + 2 * ks, idS, ks > 0);   // q_hi k_hi + q_hi k_lo
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem_S, dA2 + 2 * ks, dK + 2 * ks, idS, 1);        // q_lo k_hi
-        umma_commit(s_full);
+        // S(it+1) runs on the tensor core while the softmax warps work on S(it) (its TMEM buffer was drained
+        // before p_full(it-1), which this thread has already observed) -- but only if K(it+1) has landed:
+        // otherwise P V(it) goes first so that its stage is released and the loader keeps prefetching.
+        bool s_next = it + 1 >= nt;
+        if (!s_next && mbar_test_wait(kv_full0 + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1)) { issue_S(it + 1); s_next = true; }
         mbar_wait(p_full, it & 1);
         tc_fence_after();
         const uint64_t dVh = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128));
@@ -240,6 +264,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         }
         umma_commit(o_full);
         umma_commit(kv_empty0 + 8 * s);
+        if (!s_next) issue_S(it + 1);
       }
     }
     __syncwarp();
