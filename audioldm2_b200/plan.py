@@ -263,9 +263,10 @@ class Planner:
              bn: Optional[int] = None, m_rows: Optional[int] = None) -> WMat:
         N, K = wm.shape
         assert K == ntaps * cp
-        # narrow tiles only pay for short K loops; long-K (deep conv) GEMMs keep 128-wide tiles + split-K,
-        # which moves half the operand bytes
-        bn = bn or self.bn_for_rows(N, m_rows if K <= 2048 else None, geglu)
+        # Measured (profiles/r01_unet_ops_v4_eager.csv vs v5): narrower tiles for small-M GEMMs are SLOWER
+        # (more CTAs re-read the same activation rows, MMA N=32/64 is less efficient), so the widest tile
+        # that divides N is always used; m_rows is kept for future tuning.
+        bn = bn or self.bn_for_rows(N, None, geglu)
         if geglu:
             order = packing.geglu_row_order(N // 2, bn)
             wm = wm[order]
