@@ -155,7 +155,10 @@ def run_reference_arm(a):
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload=f"{a.model}, 1 prompt, {a.ddim_steps} DDIM steps, 10 s @16 kHz (bounded CPU sample)"),
+                config=dict(workload=f"{a.model}, batch {a.batch} prompts/GPU, {a.ddim_steps} DDIM steps, 10 s @16 kHz, cfg 3.5, eta 1.0, "
+                                     f"n_candidate_gen_per_text=1, T5 len {a.t5_len}",
+                            note="CPU arm: clips are independent, so each step times a bounded B=1 sample of this workload "
+                                 "(see cpu_baseline.sample) and reports clips/s on the host cores"),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -247,7 +250,7 @@ def kernel_pass(eng, peaks: dict, dump=None):
     peak = peaks.get("bf16_tflops_sustained") or 1432.6
     ach = fl / (tm * 1e-3) / 1e12 if tm > 0 else 0.0
     return dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
-                kernel="gemm_tc_kernel (bf16x3: 3 tcgen05 MMAs per algorithmic MAC)",
+                kernel="gemm_tc3_kernel (persistent tcgen05 implicit GEMM, bf16x3: 3 tensor MACs per algorithmic MAC, so frac <= 1/3)",
                 peak_source=("MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"),
                 share_of_unet_step={k: round(v / total, 4) for k, v in per_kind.items()},
                 unet_eval_ms_eager=round(total, 3))
