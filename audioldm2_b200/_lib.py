@@ -24,6 +24,7 @@ ABI_VERSION = 4
 
 # enums (keep in sync with the header; checked by tests/test_abi.py against the header text)
 GEMM_TC, GEMM_SIMT, GEMM_TC_V1 = 0, 1, 2
+GEMM_STATIC_B = 1 << 16
 ACT_NONE, ACT_GEGLU, ACT_TANH, ACT_SILU = 0, 1, 2, 3
 OUT_F32, OUT_PLANES, OUT_NCHW, OUT_QKV = 0, 1, 2, 3
 PREP_COPY, PREP_SILU, PREP_LRELU, PREP_GN, PREP_GN_SILU, PREP_LN = 0, 1, 2, 3, 4, 5

@@ -5,7 +5,7 @@
 // tiles of 64.  Operands are the bf16 hi/lo planes written by the projection GEMMs
 // (ALDM_OUT_QKV): Q, K row-major, V already transposed (keys contiguous), so every operand tile is
 // a plain cp.async copy into the same 128-byte-swizzled K-major layout the GEMM uses.
-//   S = Q K^T       : [q_hi|q_hi] x [k_hi|k_lo]^T (K=64) + [q_lo] x [k_hi]^T (K=32)   -> TMEM (6 UMMAs)
+//   S = Q K^T       : q_hi k_hi^T + q_hi k_lo^T + q_lo k_hi^T, 2 K-steps of 16 each      -> TMEM (6 UMMAs)
 //   softmax          : 128 threads, one query row each (TMEM lane == row), online max/sum in the
 //                      log2 domain, P split to bf16 hi/lo and written to shared memory as the A operand
 //   O_tile = P V     : 3 passes x 4 K-steps, N = 32                                    -> TMEM (12 UMMAs)
@@ -17,6 +17,7 @@
 // attention_simt_kernel: CUDA-core checker on the same operands (validation only).
 // softmax_rows_kernel: row softmax for the VAE AttnBlock (model.py:216-217).
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,25 +36,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 namespace atc {
 constexpr int QT = 128, KT = 64;
-constexpr int QA1 = 0;                         // [128][128B]  q_hi | q_hi
-constexpr int QA2 = QA1 + QT * 128;            // [128][128B]  q_lo | -
-constexpr int KB = QA2 + QT * 128;             // 2 x [64][128B]   k_hi | k_lo
-constexpr int VT = KB + 2 * KT * 128;          // 2 x {hi,lo} x [32][128B]
-constexpr int PP = VT + 2 * 2 * ATT_D * 128;   // {hi,lo} x [128][128B]
-constexpr int BAR = PP + 2 * QT * 128;
-constexpr int SMEM = BAR + 128 + 1024;
+// NS = number of K/V stages.  The profile of the 2-stage kernel showed the softmax warps idle 43% of the time
+// waiting for S: a stage is only released after P V(it), so K(it+2) was requested one tile period before it was
+// needed, less than the L2 latency under load.  Three stages give two periods of prefetch distance.  They fit in
+// the same 97 KB (two CTAs per SM) because Q is stored once as [q_hi | q_lo] rows: every K=16 MMA step takes its
+// own descriptor, so the three product terms just use different 32-byte offsets inside the 128-byte swizzled rows
+// (an earlier layout kept a second [q_hi | q_hi] copy to pair with [k_hi | k_lo]).
+template <int NS>
+struct Cfg {
+  static constexpr int QA = 0;                           // [128][128B]  q_hi | q_lo
+  static constexpr int KB = QA + QT * 128;               // NS x [64][128B]   k_hi | k_lo
+  static constexpr int VT = KB + NS * KT * 128;          // NS x {hi,lo} x [32][128B]
+  static constexpr int PP = VT + NS * 2 * ATT_D * 128;   // {hi,lo} x [128][128B]
+  static constexpr int BAR = PP + 2 * QT * 128;
+  static constexpr int SMEM = BAR + 128 + 1024;          // + barriers + round-up slack for the 1024-byte tile alignment
+};
 constexpr int TMEM_COLS = 256;                 // S double buffer: cols [0,64) / [64,128); O_tile: cols [128,160)
 }  // namespace atc
 
+template <int NS>
 __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_constant__ aldm_attn_desc d) {
   using namespace atc;
+  using L = Cfg<NS>;
+  constexpr int QA = L::QA, KB = L::KB, VT = L::VT, PP = L::PP;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t bar = base + BAR;
-  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 24, s_full0 = bar + 40, p_full = bar + 56,
-                 o_full = bar + 64, tmem_slot = bar + 72;
+  const uint32_t bar = base + L::BAR;
+  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = kv_full0 + 8 * NS, s_full0 = kv_empty0 + 8 * NS,
+                 p_full = s_full0 + 16, o_full = p_full + 8, tmem_slot = o_full + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
   const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
@@ -62,8 +74,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
   if (tid == 0) {
     // one arrival per WARP everywhere (per-thread arrivals on one mbarrier word serialise in the smem atomic unit)
     mbar_init(q_full, 32);
-    mbar_init(kv_full0, 32); mbar_init(kv_full0 + 8, 32);
-    mbar_init(kv_empty0, 1); mbar_init(kv_empty0 + 8, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(kv_full0 + 8 * i, 32); mbar_init(kv_empty0 + 8 * i, 1); }
     mbar_init(s_full0, 1); mbar_init(s_full0 + 8, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -71,8 +82,9 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + BAR + 72);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
   const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+  pdl_wait();
 
   if (warp < 4) {
     // =============================== softmax + output ===============================
@@ -188,14 +200,12 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
     const __nv_bfloat16* kl = reinterpret_cast<const __nv_bfloat16*>(d.k_lo);
     const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(d.vt_hi);
     const __nv_bfloat16* vl = reinterpret_cast<const __nv_bfloat16*>(d.vt_lo);
-    // Q: QA1 row r chunk c <- q_hi chunk (c & 3); QA2 row r chunk c (c < 4) <- q_lo chunk c
+    // Q: row r chunk c <- (c < 4 ? q_hi : q_lo) chunk (c & 3)
     for (int idx = lane; idx < QT * 8; idx += 32) {
       const int r = idx >> 3, c = idx & 7;
       const bool ok = q0 + r < d.Nq;
       const long long off = ok ? ((long long)b * d.Nq + q0 + r) * d.ldq + d.q_col + h * ATT_D + (c & 3) * 8 : 0;
-      const uint32_t dst = base + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4);
-      cp_async_16(dst + QA1, qh + off, ok ? 16u : 0u);
-      if (c < 4) cp_async_16(dst + QA2, ql + off, ok ? 16u : 0u);
+      cp_async_16(base + QA + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), (c < 4 ? qh : ql) + off, ok ? 16u : 0u);
     }
     cp_async_mbar_arrive_noinc(q_full);
     // K/V tiles: every lane owns one 16-byte chunk column c and rows r0 + 4i; all row bases are hoisted out of
@@ -204,9 +214,9 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
     const __nv_bfloat16* kcol = (c < 4 ? kh : kl) + (long long)bkv * d.Nk * d.ldk + d.k_col + h * ATT_D + (c & 3) * 8;
     const long long vrow0 = ((long long)(bkv * d.heads + h) * ATT_D + r0) * d.ld_t + c * 8;
     const long long kstep = 4ll * d.ldk, vstep = 4ll * d.ld_t;
-    for (int it = 0; it < nt; ++it) {
-      const int s = it & 1, k0 = it * KT;
-      mbar_wait(kv_empty0 + 8 * s, ((it >> 1) & 1) ^ 1);
+    for (int it = 0, s = 0, ph = 1; it < nt; ++it) {
+      const int k0 = it * KT;
+      mbar_wait(kv_empty0 + 8 * s, ph);
       const uint32_t kb = base + KB + s * (KT * 128);
       const __nv_bfloat16* kp = kcol + (long long)(k0 + r0) * d.ldk;
 #pragma unroll
@@ -224,34 +234,38 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         cp_async_16(vb + pl * (ATT_D * 128) + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), vok ? vp : vh, vok ? 16u : 0u);
       }
       cp_async_mbar_arrive_noinc(kv_full0 + 8 * s);
+      if (++s == NS) { s = 0; ph ^= 1; }
     }
   } else {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idS = umma_idesc_bf16(128, KT), idO = umma_idesc_bf16(128, ATT_D);
-      const uint64_t dA1 = umma_desc_sw128(base + QA1), dA2 = umma_desc_sw128(base + QA2);
+      const uint64_t dQ = umma_desc_sw128(base + QA);
       const uint64_t dPh = umma_desc_sw128(base + PP), dPl = umma_desc_sw128(base + PP + QT * 128);
       auto issue_S = [&](int t) {      // S(t) = Q K(t)^T into TMEM buffer t & 1
-        const int st = t & 1;
-        mbar_wait(kv_full0 + 8 * st, (t >> 1) & 1);      // returns at once when the caller has already seen it complete
+        const int st = t % NS;
+        mbar_wait(kv_full0 + 8 * st, (t / NS) & 1);      // returns at once when the caller has already seen it complete
         tc_fence_after();
         const uint64_t dK = umma_desc_sw128(base + KB + st * (KT * 128));
-        const uint32_t tS = tmem_S + st * KT;
+        const uint32_t tS = tmem_S + (t & 1) * KT;
+        // descriptor address units are 16 bytes: +2 = next K-step of 16 bf16, +4 = the lo half of the row
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_bf16(tS, dA1 + 2 * ks, dK + 2 * ks, idS, ks > 0);   // q_hi k_hi + q_hi k_lo
+        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dQ + 4 + 2 * ks, dK + 2 * ks, idS, ks > 0);     // q_lo k_hi
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dA2 + 2 * ks, dK + 2 * ks, idS, 1);        // q_lo k_hi
-        umma_commit(s_full0 + 8 * st);
+        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dQ + 2 * ks, dK + 4 + 2 * ks, idS, 1);          // q_hi k_lo
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dQ + 2 * ks, dK + 2 * ks, idS, 1);              // q_hi k_hi
+        umma_commit(s_full0 + 8 * (t & 1));
       };
       mbar_wait(q_full, 0);
       issue_S(0);
       for (int it = 0; it < nt; ++it) {
-        const int s = it & 1;
+        const int s = it % NS;
         // S(it+1) runs on the tensor core while the softmax warps work on S(it) (its TMEM buffer was drained
         // before p_full(it-1), which this thread has already observed) -- but only if K(it+1) has landed:
         // otherwise P V(it) goes first so that its stage is released and the loader keeps prefetching.
         bool s_next = it + 1 >= nt;
-        if (!s_next && mbar_test_wait(kv_full0 + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1)) { issue_S(it + 1); s_next = true; }
+        if (!s_next && mbar_test_wait(kv_full0 + 8 * ((it + 1) % NS), ((it + 1) / NS) & 1)) { issue_S(it + 1); s_next = true; }
         mbar_wait(p_full, it & 1);
         tc_fence_after();
         const uint64_t dVh = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128));
@@ -266,6 +280,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         umma_commit(kv_empty0 + 8 * s);
         if (!s_next) issue_S(it + 1);
       }
+      pdl_launch();     // last P V issued: schedule the next kernel's blocks under this CTA's tail
     }
     __syncwarp();
   }
@@ -331,13 +346,20 @@ int attention_launch(const aldm_attn_desc& d, cudaStream_t st) {
     dim3 grid(cdiv(d.Nq, 128), d.heads, d.B);
     attention_simt_kernel<<<grid, 128, 0, st>>>(d);
   } else {
-    static bool configured = false;
-    if (!configured) {
-      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM));
-      configured = true;
+    static int stages = 0;
+    if (stages == 0) {
+      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<2>::SMEM));
+      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<3>::SMEM));
+      // three K/V stages only if two CTAs still fit on an SM (they do on B200: 2 x 114 KB); ALDM_ATTN_STAGES=2 forces the old layout
+      int occ = 0;
+      ALDM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tc_kernel<3>, 192, atc::Cfg<3>::SMEM));
+      const char* e = getenv("ALDM_ATTN_STAGES");
+      stages = (occ >= 2 && !(e && e[0] == '2')) ? 3 : 2;
+      if (getenv("ALDM_VERBOSE")) fprintf(stderr, "[aldm] attention_tc: %d K/V stages (occupancy of the 3-stage kernel: %d CTAs/SM)\n", stages, occ);
     }
     dim3 grid(cdiv(d.Nq, atc::QT), d.heads, d.B);
-    attention_tc_kernel<<<grid, 192, atc::SMEM, st>>>(d);
+    if (stages == 3) ALDM_CHECK_CUDA(launch_pdl(attention_tc_kernel<3>, grid, dim3(192), atc::Cfg<3>::SMEM, st, d));
+    else ALDM_CHECK_CUDA(launch_pdl(attention_tc_kernel<2>, grid, dim3(192), atc::Cfg<2>::SMEM, st, d));
   }
   ALDM_CHECK_CUDA(cudaGetLastError());
   return ALDM_OK;

@@ -33,6 +33,36 @@ void set_error(const char* fmt, ...);
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// Every kernel of the per-step programs is launched with programmatic stream serialisation: it may
+// start (block scheduling, barrier init, TMEM allocation, index set-up) while its predecessor drains,
+// and calls pdl_wait() before its first global-memory access, which blocks until the predecessor has
+// completed and flushed.  Because every such kernel waits, completion stays transitive along the
+// stream (kernel k+2 cannot pass its wait before kernel k is done).  pdl_launch() is issued LATE (last MMA
+// issued / last loads done): triggering at kernel entry made small dependent blocks co-resident with the
+// primary for its whole run time and measurably slowed it (+1.5 ms per DDIM step; split-K GEMM + reduction
+// pair +12 us), so the early start is limited to the primary's tail.  It must also come AFTER any TMEM
+// allocation (a dependent CTA that grabbed TMEM first could starve a still-unallocated primary CTA).
+// ALDM_PDL=0 in the environment disables the launch attribute (the device instructions are then no-ops).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // bf16 hi/lo split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|
 // ------------------------------------------------------------------------------------------

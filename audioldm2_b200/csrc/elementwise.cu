@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const float4* __restrict
                                                         const float4* __restrict__ ec, const float4* __restrict__ nz,
                                                         float4* __restrict__ xp, float4* __restrict__ px0,
                                                         long long n4, DdimCoef c) {
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 X = __ldcs(x + i), U = __ldcs(eu + i), Cn = __ldcs(ec + i), Z = __ldcs(nz + i);
     float4 P, O;
@@ -47,6 +48,7 @@ __global__ void masked_blend_kernel(float* __restrict__ img, const float* __rest
 
 __global__ void temb_kernel(const long long* __restrict__ t, int B, int dim, const float* __restrict__ freqs,
                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_wait();
   const int half = dim >> 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * half) return;
@@ -65,6 +67,7 @@ __global__ void temb_kernel(const long long* __restrict__ t, int B, int dim, con
 
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int to_nhwc,
                                  long long n) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // i indexes dst

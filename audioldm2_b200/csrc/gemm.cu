@@ -16,6 +16,8 @@
 //   warp 4     B producer: one elected lane issues a TMA bulk copy (cp.async.bulk) of the
 //              host-packed, pre-swizzled weight tile image (hi|lo) per stage.
 //   warp 5     allocates TMEM; one elected lane issues tcgen05.mma and commits stages.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aldm {
@@ -222,6 +224,70 @@ __device__ __forceinline__ void epi_finish_coalesced(const aldm_gemm_desc& d, co
       split2(x[2], x[3], h.y, l.y);
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + n) = h;
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + n) = l;
+    }
+  }
+  __syncwarp();
+}
+
+// ---- compact coalesced finish (EPI_F32N / EPI_PLN / EPI_GEGLU) -----------------------------------
+// Same idea as above with a quarter of the instructions: the staging tile is 32 rows x 128 bytes with the
+// 16-byte chunk index XOR-swizzled by (row & 7), so both the row-owner writes and the transposed reads are
+// conflict-free 128-bit accesses (8 STS.128 + 8 LDS.128 per lane instead of 32 + 32 scalar ones); bias is
+// added after the transpose (one float4 per lane and chunk, fetched before the accumulator is ready), the
+// output mode is a template parameter, and alpha / accumulate / rowvec are not supported (host-checked).
+struct CoRows32 {       // host guarantees rows * max(ldo, ld_res) < 2^31 on this path
+  int orow[8];
+  unsigned vmask;
+};
+
+__device__ __forceinline__ CoRows32 co_rows32(const RowInfo& r, int lane) {
+  CoRows32 cr;
+  cr.vmask = __ballot_sync(0xffffffffu, r.valid);
+  const int rs = lane >> 3;
+  const int o = (int)r.orow;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) cr.orow[it] = __shfl_sync(0xffffffffu, o, it * 4 + rs);
+  return cr;
+}
+
+__device__ __forceinline__ void co_load_res32(const aldm_gemm_desc& d, const CoRows32& cr, int n0, int n_out, int lane, float4 (&rv)[8]) {
+  const int rs = lane >> 3, n = n0 + (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const bool ok = ((cr.vmask >> (it * 4 + rs)) & 1u) && n < n_out;
+    rv[it] = ok ? __ldg(reinterpret_cast<const float4*>(d.res + (cr.orow[it] * d.ld_res + n))) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void stage_rows(uint8_t* stg, int lane, const float* v) {
+  uint8_t* wr = stg + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(wr + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+}
+
+template <bool PLANES_ONLY, typename CR>
+__device__ __forceinline__ void emit_rows(const aldm_gemm_desc& d, const CR& cr, int n0, int n_out, const uint8_t* stg,
+                                          int lane, const float4 (&rv)[8], bool has_rv, float4 b4) {
+  const int rs = lane >> 3, c8 = lane & 7;
+  const int n = n0 + c8 * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rs;
+    float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c8 ^ (rr & 7)) << 4));
+    if (!((cr.vmask >> rr) & 1u) || n >= n_out) continue;
+    x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+    if (has_rv) { x.x += rv[it].x; x.y += rv[it].y; x.z += rv[it].z; x.w += rv[it].w; }
+    const auto o = cr.orow[it] * d.ldo + n;      // 32-bit on the compact path, 64-bit for GEGLU (CoRows)
+    if (!PLANES_ONLY) *reinterpret_cast<float4*>(d.out + o) = x;
+    if (PLANES_ONLY || d.out_hi) {
+      uint2 h, l;
+      split2(x.x, x.y, h.x, l.x);
+      split2(x.z, x.w, h.y, l.y);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + o) = h;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + o) = l;
     }
   }
   __syncwarp();
@@ -449,7 +515,7 @@ __device__ long long g_timeline[4 * 256 * 2];
 // Tile order: split-K slice fastest, then n-tile, then m-tile, so CTAs running concurrently share the
 // same activation rows in L2.
 // ------------------------------------------------------------------------------------------
-enum { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2 };
+enum { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2, EPI_F32N = 3, EPI_PLN = 4 };
 
 // Division by a launch-time constant as multiply + shift (n < 2^31, d < 2^31): q = (n * M) >> (32 + l),
 // M = floor(2^(32+l) / d) + 1, l = ceil(log2 d).  The persistent roles run one warp per scheduler, so a
@@ -473,7 +539,10 @@ static FastDiv make_fastdiv(int d) {
   if (d == 1) { f.M = 1ull << 32; f.sh = 32; }
   return f;
 }
-struct Tc3Divs { FastDiv ow, oh, cp, tn, bmod; };
+struct Tc3Divs {
+  FastDiv ow, oh, cp, tn, bmod;
+  int plain;      // 1x1 tap, unit stride, no upsample / batch-modulo: input row == output row (linear layers)
+};
 
 template <int BN>
 struct Tc3Cfg : TcCfg<BN> {
@@ -524,6 +593,10 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Everything above overlapped the predecessor's tail; nothing below may touch its outputs before the wait.
+  // The weight stream is the exception (ALDM_GEMM_STATIC_B): warp 4 starts filling the pipeline right away.
+  // The A producers wait inside their branch, after the (memory-free) row decode of their first tile.
+  if (warp > 4 || (warp == 4 && !(d.impl & ALDM_GEMM_STATIC_B))) pdl_wait();
 
   auto tile_coords = [&](int id, int& mt, int& nt, int& z, int& kb0, int& nkb) {
     int r = id;
@@ -550,35 +623,51 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     int rowoff[8];            // element offset of tap (0,0) / channel 0 of each row (valid rows only)
     uint32_t tapmask[8];      // bit t set <=> tap t of this row is inside the input
     int ih0[8], iw0[8], pbh[8];   // only used by the nearest-upsample (up = 1) slow path
+    // Row decode of one M tile.  A single warp per scheduler runs this dependent integer chain at ~1 instruction
+    // per 6-8 cycles, and the timeline showed ~5,000 idle tensor-core cycles at every tile boundary of the K = 256
+    // linear layers because of it: linear layers take the trivial branch, and the first tile is decoded before the
+    // programmatic-dependency wait (under the previous kernel's tail).
+    auto decode_rows = [&](int mt) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = mt * C::BM + rbase + 16 * i;
+        uint32_t msk = 0;
+        int off = 0;
+        ih0[i] = 0; iw0[i] = 0; pbh[i] = -1;
+        if (fd.plain) {
+          if (m < M) { msk = 1u; off = m * d.Cp; }
+        } else if (m < M) {
+          int t, ow, b, oh;
+          fd.ow.divmod(m, t, ow);
+          fd.oh.divmod(t, b, oh);
+          const int y0 = oh * d.sy, x0 = ow * d.sx;
+          int bs = b;
+          if (d.bmod > 0) { int q; fd.bmod.divmod(b, q, bs); }
+          const int pb = bs * Hs;
+          ih0[i] = y0; iw0[i] = x0; pbh[i] = pb;
+          for (int tp = 0; tp < d.ntaps; ++tp) {
+            const int ih = y0 + d.dy[tp], iw = x0 + d.dx[tp];
+            if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) msk |= 1u << tp;
+          }
+          off = ((pb + y0) * Ws + x0) * d.Cp;
+        }
+        tapmask[i] = msk;
+        rowoff[i] = off;
+      }
+    };
+    if ((int)blockIdx.x < total) {
+      int mt, nt, z, kb0, nkb;
+      tile_coords(blockIdx.x, mt, nt, z, kb0, nkb);
+      decode_rows(mt);
+      last_mt = mt;
+    }
+    pdl_wait();
     for (int id = blockIdx.x; id < total; id += gridDim.x) {
       int mt, nt, z, kb0, nkb;
       tile_coords(id, mt, nt, z, kb0, nkb);
       if (mt != last_mt) {
         last_mt = mt;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = mt * C::BM + rbase + 16 * i;
-          uint32_t msk = 0;
-          int off = 0;
-          ih0[i] = 0; iw0[i] = 0; pbh[i] = -1;
-          if (m < M) {
-            int t, ow, b, oh;
-            fd.ow.divmod(m, t, ow);
-            fd.oh.divmod(t, b, oh);
-            const int y0 = oh * d.sy, x0 = ow * d.sx;
-            int bs = b;
-            if (d.bmod > 0) { int q; fd.bmod.divmod(b, q, bs); }
-            const int pb = bs * Hs;
-            ih0[i] = y0; iw0[i] = x0; pbh[i] = pb;
-            for (int tp = 0; tp < d.ntaps; ++tp) {
-              const int ih = y0 + d.dy[tp], iw = x0 + d.dx[tp];
-              if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) msk |= 1u << tp;
-            }
-            off = ((pb + y0) * Ws + x0) * d.Cp;
-          }
-          tapmask[i] = msk;
-          rowoff[i] = off;
-        }
+        decode_rows(mt);
       }
       // (tap, c) of this thread's 8-channel chunk at the first k-block of the tile, then advanced by 64 per block
       const int k = kb0 * C::BK + j * 8;
@@ -677,6 +766,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         }
         umma_commit(tfull_bar(acc));
       }
+      pdl_launch();     // all MMAs of this CTA are issued: let the next kernel's blocks be scheduled under the last epilogue
     }
     __syncwarp();
   } else {
@@ -700,7 +790,23 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         fd.oh.divmod(t, r.b, r.oh);
         r.orow = ((long long)r.b * d.OHF + (long long)r.oh * d.osy + d.ooy) * d.OWF + r.ow;
       }
-      const CoRows cr = co_rows(r, lane);
+      constexpr bool kCompact = EPI == EPI_F32N || EPI == EPI_PLN;
+      CoRows cr;
+      CoRows32 cr32;
+      if (kCompact) cr32 = co_rows32(r, lane); else cr = co_rows(r, lane);
+      // compact epilogues: bias and the first chunk's residual are fetched while the tile is still being accumulated
+      constexpr int NCH = BN > 64 ? 2 : 1;
+      uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);
+      float4 pb4[NCH], prv[NCH][8];
+      const bool has_res = kCompact && d.res != nullptr;
+      if (kCompact && d.splitk == 1) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int n = nt * BN + half * 32 + 64 * ch + (lane & 7) * 4;
+          pb4[ch] = (d.bias && n < d.N) ? __ldg(reinterpret_cast<const float4*>(d.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (has_res && half * 32 < BN) co_load_res32(d, cr32, nt * BN + half * 32, d.N, lane, prv[0]);
+      }
       mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
       if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
       tc_fence_after();
@@ -746,7 +852,27 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           if (d.bias) { add_vec32(v, d.bias + nt * BN + c0); add_vec32(g, d.bias + nt * BN + BN / 2 + c0); }
 #pragma unroll      // full unroll: v/g must stay in registers (a partial unroll indexes them dynamically -> local memory)
           for (int i = 0; i < 32; ++i) v[i] *= gelu_f(g[i]);
-          epi_finish_coalesced(d, cr, n0, v, n_out, stg, lane, rv, false);
+          if (d.out_mode == ALDM_OUT_PLANES) {      // the FF1 case: operand planes for FF2
+            stage_rows(stg8, lane, v);
+            emit_rows<true>(d, cr, n0, n_out, stg8, lane, rv, false, make_float4(0.f, 0.f, 0.f, 0.f));
+          } else {
+            epi_finish_coalesced(d, cr, n0, v, n_out, stg, lane, rv, false);
+          }
+        }
+      } else if (kCompact) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c0 = half * 32 + 64 * ch;
+          if (c0 < BN) {
+            const int n0 = nt * BN + c0;
+            uint32_t vr[32];
+            tmem_ld32(trow + c0, vr);
+            tmem_ld_wait();
+            stage_rows(stg8, lane, reinterpret_cast<const float*>(vr));
+            // the next chunk's residual is in flight while this one is written out
+            if (ch + 1 < NCH && has_res && c0 + 64 < BN) co_load_res32(d, cr32, n0 + 64, d.N, lane, prv[(ch + 1) % NCH]);
+            emit_rows<EPI == EPI_PLN>(d, cr32, n0, d.N, stg8, lane, prv[ch], has_res, pb4[ch]);
+          }
         }
       } else if (EPI == EPI_FAST) {
         // no activation; fp32 / planes / dual / QKV outputs, all through the coalesced path (host-checked)
@@ -828,6 +954,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
 // split-K reduction + epilogue
 // ------------------------------------------------------------------------------------------
 __global__ void splitk_epilogue_kernel(const __grid_constant__ aldm_gemm_desc d, int Mpad, int Npad) {
+  pdl_wait();
   const int M = d.B * d.OH * d.OW;
   const int chunks_per_row = (d.act == ALDM_ACT_GEGLU) ? (Npad / d.bn) * (d.bn / 64) : Npad / 32;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -966,12 +1093,15 @@ static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   Tc3Divs fd;
   fd.ow = make_fastdiv(d.OW); fd.oh = make_fastdiv(d.OH); fd.cp = make_fastdiv(d.Cp); fd.tn = make_fastdiv(tiles_n);
   fd.bmod = make_fastdiv(d.bmod > 0 ? d.bmod : 1);
-  gemm_tc3_kernel<BN, EPI><<<grid, 448, C::SMEM_BYTES, st>>>(d, tiles_m, tiles_n, fd);
+  fd.plain = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.sy == 1 && d.sx == 1 && d.up == 0 && d.bmod <= 0 &&
+             d.OH == d.H && d.OW == d.W;
+  ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd));
   ALDM_CHECK_CUDA(cudaGetLastError());
   if (d.splitk > 1) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
     const int chunks = (d.act == ALDM_ACT_GEGLU) ? (Npad / BN) * (BN / 64) : Npad / 32;
     const long long tot = (long long)M * chunks;
+    // plain launch (full serialisation): early-scheduled reduction blocks only disturbed the GEMM's last epilogue
     splitk_epilogue_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d, Mpad, Npad);
     ALDM_CHECK_CUDA(cudaGetLastError());
   }
@@ -986,6 +1116,15 @@ static int launch_tc2(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   const bool co = d.splitk == 1 && n_out % 4 == 0 && d.ldo % 4 == 0 && (!d.res || d.ld_res % 4 == 0) &&
                   (d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_PLANES || d.out_mode == ALDM_OUT_QKV);
   if (co && geglu && !d.res && d.out_mode != ALDM_OUT_QKV && BN >= 64) return launch_tc3_epi<BN, EPI_GEGLU>(d, M, st);
+  const long long out_rows = (long long)d.B * d.OHF * d.OWF;
+  const int ld_max = d.ldo > d.ld_res ? d.ldo : d.ld_res;
+  static const bool compact_on = [] { const char* e = getenv("ALDM_EPI_COMPACT"); return !(e && e[0] == '0'); }();   // A/B switch
+  const bool plain = compact_on && co && d.act == ALDM_ACT_NONE && d.alpha == 1.0f && !d.accumulate && !d.rowvec &&
+                     out_rows * ld_max < (1ll << 31) &&
+                     (!d.bias || aligned16(d.bias)) && (!d.res || aligned16(d.res));
+  if (plain && d.out_mode == ALDM_OUT_F32 && aligned16(d.out) && (!d.out_hi || d.ldo % 4 == 0))
+    return launch_tc3_epi<BN, EPI_F32N>(d, M, st);
+  if (plain && d.out_mode == ALDM_OUT_PLANES) return launch_tc3_epi<BN, EPI_PLN>(d, M, st);
   if (co && d.act == ALDM_ACT_NONE) return launch_tc3_epi<BN, EPI_FAST>(d, M, st);
   return launch_tc3_epi<BN, EPI_GENERIC>(d, M, st);
 }

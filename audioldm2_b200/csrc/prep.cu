@@ -25,6 +25,7 @@ __device__ __forceinline__ float4 load_cat4(const aldm_prep_desc& d, long long r
 // GroupNorm statistics: grid (nblk, B); block 256.  partial[b][blk][g] = (sum, sumsq) as doubles.
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __grid_constant__ aldm_prep_desc d, int nblk) {
+  pdl_wait();
   __shared__ double s_sum[32], s_sq[32];
   const int b = blockIdx.y, blk = blockIdx.x;
   const int C = d.c0 + d.c1, Q = C >> 2, cpg = C / d.groups;
@@ -71,6 +72,7 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* hp, __nv_bfloat16* 
 
 // grid (nblk_apply, B); block 256
 __global__ void gn_apply_kernel(const __grid_constant__ aldm_prep_desc d, int nblk_stats) {
+  pdl_wait();
   __shared__ float s_scale[GN_MAX_C], s_shift[GN_MAX_C];
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.y;
@@ -121,6 +123,7 @@ __global__ void gn_apply_kernel(const __grid_constant__ aldm_prep_desc d, int nb
 // LayerNorm: one warp per row, C % 4 == 0, C <= 1024
 // ---------------------------------------------------------------------------------------------
 __global__ void ln_kernel(const __grid_constant__ aldm_prep_desc d) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= d.rows) return;
@@ -138,6 +141,7 @@ __global__ void ln_kernel(const __grid_constant__ aldm_prep_desc d) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / C;
+  pdl_launch();      // late trigger: the row is in registers; see common.cuh on why not at kernel entry
   float s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -172,6 +176,7 @@ __global__ void ln_kernel(const __grid_constant__ aldm_prep_desc d) {
 // elementwise copy / SiLU / leaky-ReLU -> planes; one thread per (row, 8-channel chunk)
 // ---------------------------------------------------------------------------------------------
 __global__ void ew_kernel(const __grid_constant__ aldm_prep_desc d) {
+  pdl_wait();
   const int C = d.c0 + d.c1;
   const int chunks = d.Cp >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,6 +205,7 @@ __global__ void ew_kernel(const __grid_constant__ aldm_prep_desc d) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = y[e] > 0.f ? y[e] : y[e] * d.slope;
   }
+  pdl_launch();
   uint4 h, l;
   split8(y, h, l);
   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + row * d.Cp + c) = h;
@@ -212,6 +218,7 @@ __global__ void ew_kernel(const __grid_constant__ aldm_prep_desc d) {
 // coalesced float4 rows, one shared-memory reduction per thread at the end.
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_stats_col_kernel(const __grid_constant__ aldm_prep_desc d, int nblk) {
+  pdl_wait();
   __shared__ float s_sum[32], s_sq[32];
   const int b = blockIdx.y, blk = blockIdx.x;
   const int C = d.c0 + d.c1, Q = C >> 2, cpg = C / d.groups;
@@ -230,6 +237,7 @@ __global__ void gn_stats_col_kernel(const __grid_constant__ aldm_prep_desc d, in
     atomicAdd(&s_sum[g], a);
     atomicAdd(&s_sq[g], a2);
   }
+  pdl_launch();
   __syncthreads();
   if (threadIdx.x < d.groups) {
     double* p = d.scratch + (((long long)b * nblk + blk) * d.groups + threadIdx.x) * 2;
@@ -239,6 +247,7 @@ __global__ void gn_stats_col_kernel(const __grid_constant__ aldm_prep_desc d, in
 }
 
 __global__ void gn_apply_col_kernel(const __grid_constant__ aldm_prep_desc d, int nblk_stats) {
+  pdl_wait();
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.y;
   const int C = d.c0 + d.c1, Q = C >> 2, cpg = C / d.groups;
@@ -303,33 +312,33 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
       int nblk = cdiv(d.HW, 8);
       if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;
       const int thr = (C / 4) >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
-      gn_stats_col_kernel<<<dim3(nblk, d.B), thr, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(launch_pdl(gn_stats_col_kernel, dim3(nblk, d.B), dim3(thr), 0, st, d, nblk));
       ALDM_CHECK_CUDA(cudaGetLastError());
       int nap = cdiv(d.HW, 4);
       if (nap > 256) nap = 256;
-      gn_apply_col_kernel<<<dim3(nap, d.B), thr, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(launch_pdl(gn_apply_col_kernel, dim3(nap, d.B), dim3(thr), 0, st, d, nblk));
       ALDM_CHECK_CUDA(cudaGetLastError());
     } else {
       int nblk = cdiv(d.HW, 32);
       if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;
-      gn_stats_kernel<<<dim3(nblk, d.B), 256, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(nblk, d.B), dim3(256), 0, st, d, nblk));
       ALDM_CHECK_CUDA(cudaGetLastError());
       int nap = cdiv(d.HW, 16);
       if (nap > 128) nap = 128;
-      gn_apply_kernel<<<dim3(nap, d.B), 256, 0, st>>>(d, nblk);
+      ALDM_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(nap, d.B), dim3(256), 0, st, d, nblk));
       ALDM_CHECK_CUDA(cudaGetLastError());
     }
   } else if (d.mode == ALDM_PREP_LN) {
     ALDM_REQUIRE(d.gamma && d.beta, ALDM_E_ARG, "prep LN: null gamma/beta");
     ALDM_REQUIRE(d.c1 == 0 && C % 4 == 0 && C <= 1024 && d.Cp == C, ALDM_E_UNSUPPORTED, "prep LN: C=%d", C);
-    ln_kernel<<<cdiv(d.rows, 8), 256, 0, st>>>(d);
+    ALDM_CHECK_CUDA(launch_pdl(ln_kernel, dim3(cdiv(d.rows, 8)), dim3(256), 0, st, d));
     ALDM_CHECK_CUDA(cudaGetLastError());
   } else {
     ALDM_REQUIRE(d.mode == ALDM_PREP_COPY || d.mode == ALDM_PREP_SILU || d.mode == ALDM_PREP_LRELU, ALDM_E_ARG,
                  "prep: mode=%d", d.mode);
     if (d.src_nchw) ALDM_REQUIRE(d.c1 == 0 && d.HW > 0 && d.rows % d.HW == 0, ALDM_E_SHAPE, "prep: NCHW source shape");
     const long long total = (long long)d.rows * (d.Cp >> 3);
-    ew_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d);
+    ALDM_CHECK_CUDA(launch_pdl(ew_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, d));
     ALDM_CHECK_CUDA(cudaGetLastError());
   }
   return ALDM_OK;

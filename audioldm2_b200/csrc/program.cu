@@ -3,6 +3,7 @@
 // re-launched per DDIM step (~900 kernels per UNet evaluation; the reference issues ~3,700 per step
 // from Python).  Also the misc C-ABI entry points (error string, ABI self-description).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -18,6 +19,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ALDM_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st);

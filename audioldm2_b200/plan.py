@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -229,6 +230,7 @@ class Planner:
         self.impl = {"tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT, "tc1": _lib.GEMM_TC_V1}[impl]
         self.keep_plain = keep_plain or impl == "simt"
         self.use_splitk = splitk and impl != "simt"
+        self.static_b = os.environ.get("ALDM_BPRE", "1") != "0"      # weight prefetch ahead of the PDL wait (A/B switch)
         self.n_sm = n_sm
         self.arena = Arena()
         self.pool = Pool()
@@ -365,7 +367,8 @@ class Planner:
                  B=B, H=H, W=W, Cp=a.Cp, up=up, bmod=bmod, OH=OH, OW=OW, sy=sy, sx=sx, ntaps=w.ntaps,
                  taps=[(int(dy), int(dx)) for dy, dx in taps], N=w.N, K=w.K, Kpad=w.Kpad, bn=w.bn,
                  ldo=0, ld_res=0, ld_rowvec=ld_rowvec, OHF=OH if OHF is None else OHF, OWF=OW, osy=osy, ooy=ooy,
-                 act=act, out_mode=_lib.OUT_F32, accumulate=int(accumulate), splitk=1, impl=self.impl, alpha=alpha)
+                 act=act, out_mode=_lib.OUT_F32, accumulate=int(accumulate), splitk=1,
+                 impl=self.impl | (_lib.GEMM_STATIC_B if w.packed.region == "w" and self.static_b else 0), alpha=alpha)
         if qkv is not None:          # (planes for columns < n_split, transposed planes for the rest, n_split, tokens per batch)
             pl_, vt_, n_split, tpb = qkv
             assert n_split % w.bn == 0 and n_split % 32 == 0 and pl_.Cp == n_split

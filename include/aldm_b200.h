@@ -64,6 +64,9 @@ enum {
 /* ---- GEMM / implicit-GEMM convolution ---------------------------------------------------- */
 
 enum { ALDM_GEMM_TC = 0, ALDM_GEMM_SIMT = 1, ALDM_GEMM_TC_V1 = 2 };   /* aldm_gemm_desc.impl: persistent tcgen05 | CUDA-core checker | one-tile-per-CTA tcgen05 */
+/* OR-ed into aldm_gemm_desc.impl: w_packed is never written while the program runs (model weights), so the
+ * kernel may start streaming it before its programmatic-dependency wait (overlapping the previous kernel's tail). */
+#define ALDM_GEMM_STATIC_B (1 << 16)
 enum { ALDM_ACT_NONE = 0, ALDM_ACT_GEGLU = 1, ALDM_ACT_TANH = 2, ALDM_ACT_SILU = 3 };
 enum { ALDM_OUT_F32 = 0, ALDM_OUT_PLANES = 1, ALDM_OUT_NCHW = 2, ALDM_OUT_QKV = 3 };
 
