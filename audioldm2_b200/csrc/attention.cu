@@ -350,12 +350,10 @@ int attention_launch(const aldm_attn_desc& d, cudaStream_t st) {
     if (stages == 0) {
       ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<2>::SMEM));
       ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<3>::SMEM));
-      // three K/V stages only if two CTAs still fit on an SM (they do on B200: 2 x 114 KB); ALDM_ATTN_STAGES=2 forces the old layout
-      int occ = 0;
-      ALDM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tc_kernel<3>, 192, atc::Cfg<3>::SMEM));
+      // Both layouts are 97 KB (two CTAs per SM).  cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for either
+      // (the 2-stage kernel measurably runs two per SM under ncu), so it is not consulted.  ALDM_ATTN_STAGES=2 = A/B switch.
       const char* e = getenv("ALDM_ATTN_STAGES");
-      stages = (occ >= 2 && !(e && e[0] == '2')) ? 3 : 2;
-      if (getenv("ALDM_VERBOSE")) fprintf(stderr, "[aldm] attention_tc: %d K/V stages (occupancy of the 3-stage kernel: %d CTAs/SM)\n", stages, occ);
+      stages = (e && e[0] == '2') ? 2 : 3;
     }
     dim3 grid(cdiv(d.Nq, atc::QT), d.heads, d.B);
     if (stages == 3) ALDM_CHECK_CUDA(launch_pdl(attention_tc_kernel<3>, grid, dim3(192), atc::Cfg<3>::SMEM, st, d));

@@ -246,11 +246,11 @@ class Planner:
     def vec(self, t: torch.Tensor) -> Ref:
         return Ref("w", self.arena.add(t.float().contiguous()))
 
-    def bn_for_rows(self, N: int, m_rows: Optional[int], geglu: bool = False) -> int:
+    def bn_for_rows(self, N: int, m_rows: Optional[int], geglu: bool = False, min_bn: int = 32) -> int:
         """N tile: 128 unless the GEMM is too small to give every SM a tile -- then the widest tile that
         yields >= ~0.8 * n_sm tiles (per-tile time of a short K loop is dominated by fixed latencies, so
         more, narrower tiles in flight win)."""
-        cands = [b for b in ((128, 64) if geglu else (128, 64, 32)) if N % b == 0]
+        cands = [b for b in ((128, 64) if geglu else (128, 64, 32)) if N % b == 0 and b >= min_bn]
         if not cands:
             return 128 if geglu else packing.choose_bn(N)
         if not m_rows:
@@ -268,7 +268,8 @@ class Planner:
         # Measured (profiles/r01_unet_ops_v4_eager.csv vs v5): narrower tiles for small-M GEMMs are SLOWER
         # (more CTAs re-read the same activation rows, MMA N=32/64 is less efficient), so the widest tile
         # that divides N is always used; m_rows is kept for future tuning.
-        bn = bn or self.bn_for_rows(N, None, geglu)
+        narrow = int(os.environ.get("ALDM_NARROW", "0"))       # experiment switch: smallest N tile the heuristic may pick
+        bn = bn or self.bn_for_rows(N, m_rows if narrow else None, geglu, min_bn=narrow or 32)
         if geglu:
             order = packing.geglu_row_order(N // 2, bn)
             wm = wm[order]
