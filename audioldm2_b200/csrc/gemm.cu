@@ -994,6 +994,45 @@ __global__ void splitk_epilogue_kernel(const __grid_constant__ aldm_gemm_desc d,
   epi_finish(d, r, n0, 32, v, n_out);
 }
 
+// Coalesced variant for the cases the planner actually splits (no activation, alpha = 1, no accumulate; fp32,
+// planes or dual output; bias / row vector / residual): one thread per (row, 4 columns), so the partial sums,
+// the residual and the outputs are all full-line float4 streams.  The row-owner kernel above took 22 us per
+// launch in the step's launch list (34 launches per DDIM step) for a few MB of traffic.
+__global__ void __launch_bounds__(256) splitk_reduce4_kernel(const __grid_constant__ aldm_gemm_desc d, int Mpad, int Npad) {
+  pdl_wait();
+  const int M = d.B * d.OH * d.OW;
+  const int q_per_row = (d.N + 3) >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * q_per_row) return;
+  const int m = (int)(idx / q_per_row);
+  const int n = (int)(idx % q_per_row) * 4;
+  const RowInfo r = decode_row(d, m, M);
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < d.splitk; ++z) {          // fixed order: deterministic
+    const float4 t = *reinterpret_cast<const float4*>(d.ws + ((long long)z * Mpad + m) * Npad + n);
+    x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+  }
+  pdl_launch();
+  if (d.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(d.bias + n)); x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
+  if (d.rowvec) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(d.rowvec + (long long)r.b * d.ld_rowvec + n));
+    x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+  }
+  if (d.res) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(d.res + r.orow * d.ld_res + n));
+    x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+  }
+  const long long o = r.orow * d.ldo + n;
+  if (d.out_mode == ALDM_OUT_F32) *reinterpret_cast<float4*>(d.out + o) = x;
+  if (d.out_mode == ALDM_OUT_PLANES || d.out_hi) {
+    uint2 h, l;
+    split2(x.x, x.y, h.x, l.x);
+    split2(x.z, x.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + o) = h;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + o) = l;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // SIMT checker: obviously-correct restatement of the same descriptor on CUDA cores (fp32 FMA).
 // One warp per output row, lanes over 32 packed columns.  Validation / debugging only.
@@ -1101,8 +1140,17 @@ static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
     const int chunks = (d.act == ALDM_ACT_GEGLU) ? (Npad / BN) * (BN / 64) : Npad / 32;
     const long long tot = (long long)M * chunks;
-    // plain launch (full serialisation): early-scheduled reduction blocks only disturbed the GEMM's last epilogue
-    splitk_epilogue_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d, Mpad, Npad);
+    const bool fast = d.act == ALDM_ACT_NONE && d.alpha == 1.0f && !d.accumulate && d.N % 4 == 0 && d.ldo % 4 == 0 &&
+                      (d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_PLANES) && (!d.res || (d.ld_res % 4 == 0 && aligned16(d.res))) &&
+                      (!d.bias || aligned16(d.bias)) && (!d.rowvec || (d.ld_rowvec % 4 == 0 && aligned16(d.rowvec))) &&
+                      (d.out_mode != ALDM_OUT_F32 || aligned16(d.out));
+    // plain launches (full serialisation): early-scheduled reduction blocks only disturbed the GEMM's last epilogue
+    if (fast) {
+      const long long q = (long long)M * ((d.N + 3) / 4);
+      splitk_reduce4_kernel<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(d, Mpad, Npad);
+    } else {
+      splitk_epilogue_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d, Mpad, Npad);
+    }
     ALDM_CHECK_CUDA(cudaGetLastError());
   }
   return ALDM_OK;
