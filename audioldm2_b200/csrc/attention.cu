@@ -289,6 +289,112 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Short key sets (cross-attention to the 8-token CLAP/GPT-2 and 32-token T5 contexts): Nk <= 32.
+// The tensor-core kernel pays its whole fixed cost (TMEM allocation, three mbarrier hand-overs, a 64-key
+// tile that is mostly padding) for ~0.1 GFLOP: 37 us per launch in the step's launch list, 32 launches
+// per DDIM step.  Here one thread owns one query, K and V of the (batch, head) sit in shared memory as
+// fp32 (hi + lo is exact in fp32), and the 2 x Nk x 32 FMAs per query run on the CUDA cores.
+// ------------------------------------------------------------------------------------------------
+template <int NKT>
+__global__ void __launch_bounds__(128) attention_short_kernel(const __grid_constant__ aldm_attn_desc d) {
+  __shared__ __align__(16) float sk[NKT][ATT_D];
+  __shared__ __align__(16) float sv[NKT][ATT_D];
+  __shared__ int sstate[NKT];        // 0 = attend, 1 = masked (-FLT_MAX fill), 2 = beyond Nk
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
+  pdl_wait();
+  {
+    const __nv_bfloat16* kh = reinterpret_cast<const __nv_bfloat16*>(d.k_hi);
+    const __nv_bfloat16* kl = reinterpret_cast<const __nv_bfloat16*>(d.k_lo);
+    const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(d.vt_hi);
+    const __nv_bfloat16* vl = reinterpret_cast<const __nv_bfloat16*>(d.vt_lo);
+    for (int idx = tid; idx < NKT * ATT_D; idx += 128) {
+      const int key = idx / ATT_D, dim = idx % ATT_D;
+      float kv = 0.f, vv = 0.f;
+      if (key < d.Nk) {
+        const long long ki = ((long long)bkv * d.Nk + key) * d.ldk + d.k_col + h * ATT_D + dim;
+        const long long vi = ((long long)(bkv * d.heads + h) * ATT_D + dim) * d.ld_t + key;
+        kv = __bfloat162float(kh[ki]) + __bfloat162float(kl[ki]);
+        vv = __bfloat162float(vh[vi]) + __bfloat162float(vl[vi]);
+      }
+      sk[key][dim] = kv;
+      sv[key][dim] = vv;
+    }
+    if (tid < NKT) sstate[tid] = tid >= d.Nk ? 2 : ((d.mask && __ldg(d.mask + (long long)bkv * d.Nk + tid) != 1.0f) ? 1 : 0);
+  }
+  __syncthreads();
+  pdl_launch();
+  const int q = blockIdx.x * 128 + tid;
+  if (q >= d.Nq) return;
+  float qv[ATT_D];
+  {
+    const long long qi = ((long long)b * d.Nq + q) * d.ldq + d.q_col + h * ATT_D;
+    const uint4* ph = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.q_hi) + qi);
+    const uint4* pl = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.q_lo) + qi);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 a = __ldg(ph + c), l = __ldg(pl + c);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {      // bf16 -> fp32 is a 16-bit shift
+        qv[c * 8 + 2 * e] = __uint_as_float(aw[e] << 16) + __uint_as_float(lw[e] << 16);
+        qv[c * 8 + 2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+      }
+    }
+  }
+  const float sl2 = d.scale * 1.4426950408889634f;
+  float sc[NKT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NKT; ++k) {
+    float acc = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < ATT_D; dd += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(&sk[k][dd]);
+      acc = fmaf(qv[dd], kk.x, acc); acc = fmaf(qv[dd + 1], kk.y, acc);
+      acc = fmaf(qv[dd + 2], kk.z, acc); acc = fmaf(qv[dd + 3], kk.w, acc);
+    }
+    const int st = sstate[k];
+    const float v = st == 0 ? acc * sl2 : (st == 1 ? -FLT_MAX : -INFINITY);   // masked_fill(-finfo.max), attention.py:356-360
+    sc[k] = v;
+    mx = fmaxf(mx, v);
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int k = 0; k < NKT; ++k) {
+    const float pk = sc[k] == -INFINITY ? 0.f : ex2_approx(sc[k] - mx);
+    sc[k] = pk;
+    l += pk;
+  }
+  float o[ATT_D];
+#pragma unroll
+  for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < NKT; ++k) {
+#pragma unroll
+    for (int dd = 0; dd < ATT_D; dd += 4) {
+      const float4 vv = *reinterpret_cast<const float4*>(&sv[k][dd]);
+      o[dd] = fmaf(sc[k], vv.x, o[dd]); o[dd + 1] = fmaf(sc[k], vv.y, o[dd + 1]);
+      o[dd + 2] = fmaf(sc[k], vv.z, o[dd + 2]); o[dd + 3] = fmaf(sc[k], vv.w, o[dd + 3]);
+    }
+  }
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int i = 0; i < ATT_D; ++i) o[i] *= inv;
+  const long long orow = (long long)b * d.Nq + q;
+  __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + h * ATT_D;
+  __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + h * ATT_D;
+#pragma unroll
+  for (int i = 0; i < ATT_D; i += 8) {
+    uint4 hh, ll;
+    split8(o + i, hh, ll);
+    *reinterpret_cast<uint4*>(hp + i) = hh;
+    *reinterpret_cast<uint4*>(lp + i) = ll;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CUDA-core checker on the same plane operands: one thread per query, fp32
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attention_simt_kernel(const __grid_constant__ aldm_attn_desc d) {
@@ -345,6 +451,11 @@ int attention_launch(const aldm_attn_desc& d, cudaStream_t st) {
   if (d.impl == ALDM_GEMM_SIMT) {
     dim3 grid(cdiv(d.Nq, 128), d.heads, d.B);
     attention_simt_kernel<<<grid, 128, 0, st>>>(d);
+  } else if (d.Nk <= 32 && !(getenv("ALDM_ATTN_SHORT") && getenv("ALDM_ATTN_SHORT")[0] == '0')) {
+    dim3 grid(cdiv(d.Nq, 128), d.heads, d.B);
+    if (d.Nk <= 8) ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<8>, grid, dim3(128), 0, st, d));
+    else if (d.Nk <= 16) ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<16>, grid, dim3(128), 0, st, d));
+    else ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<32>, grid, dim3(128), 0, st, d));
   } else {
     static int stages = 0;
     if (stages == 0) {

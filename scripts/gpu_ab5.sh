@@ -13,4 +13,4 @@ for l in open(sys.argv[1]):
 PY
 }
 timeout 300 $B > gpurun_out/ab_all.log 2>&1; pick gpurun_out/ab_all.log
-timeout 300 python scripts/prof_ops.py --reps 40 --only conv_l4_640,lin_k640_n640 2>&1 | tail -2
+ALDM_ATTN_SHORT=0 timeout 300 $B > gpurun_out/ab_noshort.log 2>&1; pick gpurun_out/ab_noshort.log

@@ -203,16 +203,18 @@ def test_gemm_vs_emulator(case, impl):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
-@pytest.mark.parametrize("case", ["self", "self_long", "cross_mask", "cross_allmasked", "ragged", "bmod"])
+@pytest.mark.parametrize("case", ["self", "self_long", "cross_mask", "cross_allmasked", "ragged", "bmod",
+                                  "cross8_bmod", "cross32", "cross_tc_33"])
 def test_attention(case, impl):
     """Q|K planes + transposed V planes -> attention kernel (tcgen05 / SIMT checker) vs the emulator."""
     g = torch.Generator().manual_seed(5)
     P = Planner(impl=impl)
     B, heads = 3, 4
     Cc = heads * 32
+    # Nk <= 32 takes the CUDA-core short-key kernel (8 / 16 / 32 key instantiations), longer sets the tcgen05 kernel
     Nq, Nk = dict(self=(200, 200), self_long=(1024, 1024), cross_mask=(70, 9), cross_allmasked=(70, 9), ragged=(33, 130),
-                  bmod=(64, 40))[case]
-    Bkv = 1 if case == "bmod" else B
+                  bmod=(64, 40), cross8_bmod=(300, 8), cross32=(130, 32), cross_tc_33=(130, 33))[case]
+    Bkv = 1 if case.endswith("bmod") else B
     selfattn = case.startswith("self")
     ldq = 2 * Cc if selfattn else Cc
     qf = F32(P.raw(B * Nq * ldq * 4), B * Nq, ldq)
@@ -235,7 +237,7 @@ def test_attention(case, impl):
             ios["mask"] = ("f32", mk, (Bkv, Nk)); ins["mask"] = m
     ao = P.planes(B * Nq, Cc)
     P.attn(qp, 0, kp, kcol, vt, ao, B=B, heads=heads, Nq=Nq, Nk=Nk, mask=mk, scale=32 ** -0.5,
-           kv_bmod=1 if case == "bmod" else 0)
+           kv_bmod=1 if case.endswith("bmod") else 0)
     pl = P.finish(ios)
     # V^T planes are written directly (in the network they come from an ALDM_OUT_QKV GEMM)
     v = torch.randn(Bkv, Cc, vt.ld_t, generator=g)
