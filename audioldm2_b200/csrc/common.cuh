@@ -86,13 +86,16 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   split2(v[6], v[7], hi.w, lo.w);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with approximate reciprocal (the IEEE division expands to ~20 instructions with a guarded slow path;
+// the GroupNorm+SiLU apply kernel is issue-bound on it).  ~2 ulp, far below the 2^-17 operand split that follows.
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // erf GELU as F.gelu default (attention.py:44).  erf via Abramowitz-Stegun 7.1.26 (|err| < 5e-7 in fp32,
 // i.e. at fp32 round-off of the GELU output): 1 RCP + 1 EX2 + 8 FMA-class instructions instead of the
 // ~40-instruction erff -- the GEGLU epilogue is issue-bound (profiles/r01_gemm_timeline_tc3.txt).
 __device__ __forceinline__ float gelu_f(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;      // rcp.approx (1 MUFU, ~1 ulp): __frcp_rn expands to MUFU + Newton step + a guarded slow-path CALL per element
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

@@ -13,4 +13,4 @@ for l in open(sys.argv[1]):
 PY
 }
 timeout 300 $B > gpurun_out/ab_all.log 2>&1; pick gpurun_out/ab_all.log
-ALDM_ATTN_SHORT=0 timeout 300 $B > gpurun_out/ab_noshort.log 2>&1; pick gpurun_out/ab_noshort.log
+timeout 300 python scripts/prof_ops.py --reps 40 --only lin_k256_n2048_geglu,lin_k640_n5120_geglu,gn_silu_l1,gn_silu_l4 2>&1 | tail -4
