@@ -15,12 +15,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaldm_b200.so")
-SOURCES = ["gemm.cu", "prep.cu", "attention.cu", "elementwise.cu", "stft.cu", "program.cu"]
+SOURCES = ["gemm.cu", "prep.cu", "attention.cu", "elementwise.cu", "stft.cu", "program.cu", "engine_abi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
 MAX_TAPS = 16
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enums (keep in sync with the header; checked by tests/test_abi.py against the header text)
 GEMM_TC, GEMM_SIMT, GEMM_TC_V1 = 0, 1, 2
@@ -106,6 +106,17 @@ class Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("tag", C.c_int32), ("u", _OpU)]
 
 
+class EngineDesc(C.Structure):
+    """aldm_engine_desc (include/aldm_b200.h): programs + their fixed I/O slots."""
+    _fields_ = [("unet_cond", C.c_void_p), ("unet_step", C.c_void_p), ("vae_dec", C.c_void_p), ("vocoder", C.c_void_p),
+                ("vae_enc", C.c_void_p), ("x_slot", C.c_void_p), ("t_slot", C.c_void_p), ("eps_slot", C.c_void_p),
+                ("ctx_slot", C.c_void_p * 2), ("mask_slot", C.c_void_p * 2), ("film_slot", C.c_void_p),
+                ("z_slot", C.c_void_p), ("mel_slot", C.c_void_p), ("voc_mel_slot", C.c_void_p), ("wave_slot", C.c_void_p),
+                ("enc_mel_slot", C.c_void_p), ("moments_slot", C.c_void_p), ("B", C.c_int32), ("latent_elems", C.c_int32),
+                ("mel_elems", C.c_int32), ("wave_len", C.c_int32), ("n_ctx", C.c_int32), ("ctx_len", C.c_int32 * 2),
+                ("ctx_dim", C.c_int32 * 2), ("film_dim", C.c_int32), ("use_graph", C.c_int32)]
+
+
 def build(verbose: bool = False, force: bool = False) -> str:
     """Compile every CUDA source for sm_100a into audioldm2_b200/libaldm_b200.so (nvcc cross-compiles
     without a GPU).  Rebuilds only when a source is newer than the library."""
@@ -167,7 +178,18 @@ def lib() -> C.CDLL:
         "aldm_program_capture": (i32, [vp, vp]),
         "aldm_program_replay": (i32, [vp, vp]),
         "aldm_program_num_launches": (i32, [vp]),
+        "aldm_program_is_captured": (i32, [vp]),
         "aldm_program_destroy": (None, [vp]),
+        "aldm_engine_create": (i32, [C.POINTER(EngineDesc), C.POINTER(vp)]),
+        "aldm_engine_destroy": (None, [vp]),
+        "aldm_engine_set_conditioning": (i32, [vp, i32, vp, vp, i32, vp, vp, i32, vp, vp]),
+        "aldm_engine_precompute": (i32, [vp, vp]),
+        "aldm_engine_unet_eps": (i32, [vp, vp, i64, vp, vp, vp]),
+        "aldm_engine_ddim_step": (i32, [vp, vp, i64, vp, f32, f32, f32, f32, f32, vp, vp, vp]),
+        "aldm_engine_vae_decode": (i32, [vp, vp, vp, vp]),
+        "aldm_engine_vocoder": (i32, [vp, vp, vp, vp]),
+        "aldm_engine_vae_encode": (i32, [vp, vp, vp, vp]),
+        "aldm_sizeof_engine_desc": (C.c_size_t, []),
         "aldm_abi_version": (i32, []),
         "aldm_sizeof_op": (C.c_size_t, []),
         "aldm_sizeof_gemm_desc": (C.c_size_t, []),
@@ -182,6 +204,8 @@ def lib() -> C.CDLL:
         fn.argtypes = args
     if L.aldm_abi_version() != ABI_VERSION:
         raise RuntimeError("libaldm_b200.so ABI version mismatch: rebuild")
+    if L.aldm_sizeof_engine_desc() != C.sizeof(EngineDesc):
+        raise RuntimeError("ctypes mirror of aldm_engine_desc does not match the C layout")
     if L.aldm_sizeof_op() != C.sizeof(Op) or L.aldm_sizeof_gemm_desc() != C.sizeof(GemmDesc):
         raise RuntimeError("ctypes mirror of aldm_op / aldm_gemm_desc does not match the C layout")
     _lib = L
@@ -192,7 +216,10 @@ EXPORTED = ["aldm_gemm", "aldm_prep", "aldm_pack_b", "aldm_attention", "aldm_sof
             "aldm_timestep_embedding", "aldm_ddim_step", "aldm_masked_blend", "aldm_transpose_chw",
             "aldm_posterior_sample", "aldm_stft_mel", "aldm_program_create", "aldm_program_run",
             "aldm_program_run_range", "aldm_program_capture", "aldm_program_replay",
-            "aldm_program_num_launches", "aldm_program_destroy", "aldm_abi_version", "aldm_sizeof_op",
+            "aldm_program_num_launches", "aldm_program_is_captured", "aldm_program_destroy", "aldm_engine_create",
+            "aldm_engine_destroy", "aldm_engine_set_conditioning", "aldm_engine_precompute", "aldm_engine_unet_eps",
+            "aldm_engine_ddim_step", "aldm_engine_vae_decode", "aldm_engine_vocoder", "aldm_engine_vae_encode",
+            "aldm_sizeof_engine_desc", "aldm_abi_version", "aldm_sizeof_op",
             "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check", "aldm_debug_timeline"]
 
 

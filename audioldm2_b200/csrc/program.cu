@@ -124,6 +124,8 @@ extern "C" int aldm_program_replay(aldm_program* p, void* stream) {
   return ALDM_OK;
 }
 
+extern "C" int aldm_program_is_captured(aldm_program* p) { return (p && p->exec) ? 1 : 0; }
+
 extern "C" int aldm_program_num_launches(aldm_program* p) {
   if (!p) return 0;
   int n = 0;
@@ -159,6 +161,7 @@ extern "C" size_t aldm_offsetof_gemm(int32_t field) {
     default: return (size_t)-1;
   }
 }
+extern "C" size_t aldm_sizeof_engine_desc(void) { return sizeof(aldm_engine_desc); }
 extern "C" const char* aldm_last_error(void) { return g_err; }
 
 extern "C" int aldm_device_check(int32_t device) {

@@ -38,7 +38,7 @@ def split_state_dict(state_dict: Dict[str, torch.Tensor]):
 class NativeLatentDiffusion:
     def __init__(self, cfg: dict, unet_sd, vae_sd, vocoder_sd, batch: int, device="cuda:0", scale_factor: float = 1.0,
                  ctx_max_len=(8, 128), impl: str = "tc", keep_plain: bool = False, use_graph: bool = True,
-                 with_encoder: bool = False, arena_bcast=None):
+                 with_encoder: bool = False, arena_bcast=None, use_engine_abi: bool = False):
         """``batch`` is the latent batch B_l = batchsize * n_candidate_gen_per_text the programs are
         planned for.  ``arena_bcast(name, cpu_or_none, nbytes) -> device tensor`` lets parallel.py
         replace the H2D upload by an NCCL broadcast from rank 0."""
@@ -75,6 +75,49 @@ class NativeLatentDiffusion:
         self.n_ctx = len([c for c in (cfg["unet"].get("context_dim") or []) if c is not None])
         self.film = cfg["unet"].get("extra_film_condition_dim") is not None
         self._t_host = torch.empty(2 * batch, dtype=torch.int64).pin_memory() if torch.cuda.is_available() else None
+        # Engine-level C-ABI (include/aldm_b200.h, aldm_engine_*): the same programs and slots driven by one C call
+        # per seam.  The Python orchestration below stays the default; tests/test_gpu_nets.py checks both agree.
+        self.use_engine_abi = use_engine_abi
+        self._engine = self._create_engine()
+
+    def _create_engine(self):
+        import ctypes as C
+        L = _lib.lib()
+        d = _lib.EngineDesc()
+        u = self.unet
+        d.unet_cond, d.unet_step = u.handles["cond"].value, u.handles["step"].value
+        d.vae_dec, d.vocoder = self.vae_dec.handles["all"].value, self.vocoder.handles["all"].value
+        d.vae_enc = self.vae_enc.handles["all"].value if self.vae_enc is not None else None
+        d.x_slot, d.t_slot, d.eps_slot = u.view("x").data_ptr(), u.view("t").data_ptr(), u.view("eps").data_ptr()
+        d.n_ctx = self.n_ctx
+        for s in range(self.n_ctx):
+            ctx = u.view(f"ctx{s}")
+            d.ctx_slot[s], d.mask_slot[s] = ctx.data_ptr(), u.view(f"mask{s}").data_ptr()
+            d.ctx_len[s], d.ctx_dim[s] = ctx.shape[1], ctx.shape[2]
+        if self.film:
+            y = u.view("y")
+            d.film_slot, d.film_dim = y.data_ptr(), y.shape[1]
+        d.z_slot, d.mel_slot = self.vae_dec.view("z").data_ptr(), self.vae_dec.view("mel").data_ptr()
+        d.voc_mel_slot, d.wave_slot = self.vocoder.view("mel").data_ptr(), self.vocoder.view("wave").data_ptr()
+        if self.vae_enc is not None:
+            d.enc_mel_slot, d.moments_slot = self.vae_enc.view("mel").data_ptr(), self.vae_enc.view("moments").data_ptr()
+        d.B = self.batch
+        d.latent_elems = int(np.prod(self.latent))
+        d.mel_elems = self.mel_hw[0] * self.mel_hw[1]
+        d.wave_len = self.vocoder.view("wave").shape[-1]
+        d.use_graph = int(self.use_graph)
+        h = C.c_void_p()
+        _lib.check(L.aldm_engine_create(C.byref(d), C.byref(h)), "engine_create")
+        self._engine_desc = d
+        return h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None):
+                _lib.lib().aldm_engine_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------------------------------
     # conditioning (DiffusionWrapper.forward's dict unpacking, ddpm.py:1821-1879)
@@ -83,6 +126,22 @@ class NativeLatentDiffusion:
         """Rows [0,B) of every conditioning buffer hold the unconditional, [B,2B) the conditional branch.
         Cross-attention K/V of every layer are computed here once per call (step-invariant)."""
         B = self.batch
+        if self.use_engine_abi:
+            L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+            keep = []
+            for half, c in ((0, uncond), (1, cond)):
+                a = [None, None, 0, None, None, 0]
+                for s_ in range(self.n_ctx):
+                    cl = c["context_list"][s_].to(self.device, torch.float32).contiguous()
+                    ml = c["mask_list"][s_].to(self.device, torch.float32).contiguous()
+                    keep += [cl, ml]
+                    a[3 * s_], a[3 * s_ + 1], a[3 * s_ + 2] = cl.data_ptr(), ml.data_ptr(), cl.shape[1]
+                y = c["y"].to(self.device, torch.float32).contiguous() if self.film else None
+                keep.append(y)
+                _lib.check(L.aldm_engine_set_conditioning(self._engine, half, *a, y.data_ptr() if y is not None else None, st),
+                           "engine_set_conditioning")
+            _lib.check(L.aldm_engine_precompute(self._engine, st), "engine_precompute")
+            return
         for s in range(self.n_ctx):
             ctx, msk = self.unet.view(f"ctx{s}"), self.unet.view(f"mask{s}")
             ctx.zero_(); msk.zero_()
@@ -100,6 +159,11 @@ class NativeLatentDiffusion:
         """Both apply_model calls of ddim.py:293-296 in one batched evaluation -> (eps_uncond, eps_cond)."""
         B = self.batch
         assert x.shape[0] == B and x.is_contiguous()
+        if self.use_engine_abi:
+            _lib.check(_lib.lib().aldm_engine_unet_eps(self._engine, x.data_ptr(), int(t), None, None,
+                                                       torch.cuda.current_stream().cuda_stream), "engine_unet_eps")
+            eps = self.unet.view("eps")
+            return eps[:B], eps[B:]
         self.unet.view("x").copy_(x, non_blocking=True)
         self.unet.view("t").fill_(int(t))
         if self.use_graph:
@@ -117,8 +181,15 @@ class NativeLatentDiffusion:
 
     def p_sample_ddim(self, x, st: dict, noise, guidance: float, out=None, pred_x0=None):
         """ddim.py:265-355: eps_u/eps_c, e = e_u + s (e_c - e_u), x_{t-1} update -- one graph replay + K6."""
-        e_u, e_c = self.apply_model_pair(x, st["t"])
         out = torch.empty_like(x) if out is None else out
+        if self.use_engine_abi:
+            assert x.is_contiguous() and noise.is_contiguous() and out.is_contiguous()
+            _lib.check(_lib.lib().aldm_engine_ddim_step(
+                self._engine, x.data_ptr(), int(st["t"]), noise.data_ptr(), st["a_t"], st["a_prev"], st["sigma_t"],
+                st["sqrt_one_minus_at"], float(guidance), out.data_ptr(), pred_x0.data_ptr() if pred_x0 is not None else None,
+                torch.cuda.current_stream().cuda_stream), "engine_ddim_step")
+            return out
+        e_u, e_c = self.apply_model_pair(x, st["t"])
         engine.ddim_step(x, e_u, e_c, noise, out, st["a_t"], st["a_prev"], st["sigma_t"], st["sqrt_one_minus_at"],
                          float(guidance), pred_x0)
         return out
@@ -131,6 +202,11 @@ class NativeLatentDiffusion:
     # ------------------------------------------------------------------------------------------
     def decode_first_stage(self, z: torch.Tensor) -> torch.Tensor:
         """ddpm.py:922-926 -> mel [B, 1, T', F'] (a view into the decoder workspace)."""
+        if self.use_engine_abi:
+            z = z.contiguous()
+            _lib.check(_lib.lib().aldm_engine_vae_decode(self._engine, z.data_ptr(), None,
+                                                         torch.cuda.current_stream().cuda_stream), "engine_vae_decode")
+            return self.vae_dec.view("mel")
         self.vae_dec.view("z").copy_(z, non_blocking=True)
         self.vae_dec.run("all")
         return self.vae_dec.view("mel")
@@ -138,6 +214,11 @@ class NativeLatentDiffusion:
     def mel_spectrogram_to_waveform(self, mel: torch.Tensor) -> torch.Tensor:
         """ddpm.py:928-939 (without the .cpu().numpy()): mel [B,1,T,F] -> waveform [B,1,L] on the device."""
         B = mel.shape[0]
+        if self.use_engine_abi:
+            m = mel.reshape(B, mel.shape[-2], mel.shape[-1]).contiguous()
+            _lib.check(_lib.lib().aldm_engine_vocoder(self._engine, m.data_ptr(), None,
+                                                      torch.cuda.current_stream().cuda_stream), "engine_vocoder")
+            return self.vocoder.view("wave")
         self.vocoder.view("mel").copy_(mel.reshape(B, mel.shape[-2], mel.shape[-1]), non_blocking=True)
         self.vocoder.run("all")
         return self.vocoder.view("wave")

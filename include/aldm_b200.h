@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define ALDM_ABI_VERSION 4
+#define ALDM_ABI_VERSION 5
 #define ALDM_MAX_TAPS 16
 
 enum {
@@ -233,14 +233,76 @@ int aldm_program_run(aldm_program* p, void* stream);            /* plain launche
 int aldm_program_run_range(aldm_program* p, int32_t first, int32_t last, void* stream);
 int aldm_program_capture(aldm_program* p, void* stream);        /* build + instantiate a CUDA graph */
 int aldm_program_replay(aldm_program* p, void* stream);         /* cudaGraphLaunch */
+int aldm_program_is_captured(aldm_program* p);                  /* 1 once aldm_program_capture succeeded */
 int aldm_program_num_launches(aldm_program* p);                 /* kernels launched per run */
 void aldm_program_destroy(aldm_program* p);
+
+/* ---- engine: the reference's seams as single calls --------------------------
+ * An engine ties the programs of one model instance to their fixed I/O slots (device addresses inside the
+ * workspace the programs were resolved against) so that a caller who is not the Python host -- or the Python
+ * host itself -- drives the hot path with the calls the reference makes:
+ *   aldm_engine_set_conditioning  <- DiffusionWrapper.forward's cond-dict unpacking (ddpm.py:1821-1879), once per call
+ *   aldm_engine_unet_eps          <- the two self.model.apply_model(x, t, c) calls of p_sample_ddim (ddim.py:293-296)
+ *   aldm_engine_ddim_step         <- DDIMSampler.p_sample_ddim as a whole (ddim.py:265-355): UNet x2 + CFG + update
+ *   aldm_engine_vae_decode        <- LatentDiffusion.decode_first_stage (ddpm.py:922-926)
+ *   aldm_engine_vocoder           <- first_stage_model.vocoder(mel) in mel_spectrogram_to_waveform (ddpm.py:928-939)
+ *   aldm_engine_vae_encode        <- encode_first_stage (ddpm.py:941-943), moments out
+ * The engine borrows the programs (it never destroys them) and owns nothing but its descriptor copy.  All
+ * pointers are device pointers, fp32 contiguous NCHW as in the reference; everything is enqueued on `stream`;
+ * nothing synchronises.  Single caller thread per engine. */
+typedef struct aldm_engine aldm_engine;
+
+typedef struct aldm_engine_desc {
+  aldm_program* unet_cond;      /* cross-attention K/V precompute (may be NULL: no cross-attention) */
+  aldm_program* unet_step;      /* one UNet evaluation of 2*B rows: rows [0,B) unconditional, [B,2B) conditional */
+  aldm_program* vae_dec;        /* may be NULL */
+  aldm_program* vocoder;        /* may be NULL */
+  aldm_program* vae_enc;        /* may be NULL */
+  float* x_slot;                /* [B, C, T, F] latent read by unet_step */
+  int64_t* t_slot;              /* [2B] DDPM timestep */
+  float* eps_slot;              /* [2B, C, T, F] */
+  float* ctx_slot[2];           /* [2B, ctx_len[i], ctx_dim[i]] zero-padded context i */
+  float* mask_slot[2];          /* [2B, ctx_len[i]] 1 = attend */
+  float* film_slot;             /* [2B, film_dim] or NULL */
+  float* z_slot;                /* vae_dec input [B, C, T, F] */
+  float* mel_slot;              /* vae_dec output [B, 1, T', F'] */
+  float* voc_mel_slot;          /* vocoder input [B, T', F'] */
+  float* wave_slot;             /* vocoder output [B, 1, L] */
+  float* enc_mel_slot;          /* vae_enc input [B, 1, T', F'] */
+  float* moments_slot;          /* vae_enc output [B, T, F, 2C] (channels-last) */
+  int32_t B;                    /* latent batch the programs were planned for */
+  int32_t latent_elems;         /* C*T*F */
+  int32_t mel_elems;            /* T'*F' */
+  int32_t wave_len;             /* L */
+  int32_t n_ctx;                /* 0..2 */
+  int32_t ctx_len[2];
+  int32_t ctx_dim[2];
+  int32_t film_dim;
+  int32_t use_graph;            /* 1: unet_step is captured on first use and replayed */
+} aldm_engine_desc;
+
+int aldm_engine_create(const aldm_engine_desc* d, aldm_engine** out);
+void aldm_engine_destroy(aldm_engine* e);
+/* which: 0 = unconditional half, 1 = conditional half.  ctx_i [B, len_i, ctx_dim[i]], mask_i [B, len_i] (fp32 0/1),
+ * len_i <= ctx_len[i]; film_y [B, film_dim] or NULL.  Call for both halves, then aldm_engine_precompute once. */
+int aldm_engine_set_conditioning(aldm_engine* e, int32_t which, const float* ctx0, const float* mask0, int32_t len0,
+                                 const float* ctx1, const float* mask1, int32_t len1, const float* film_y, void* stream);
+int aldm_engine_precompute(aldm_engine* e, void* stream);
+int aldm_engine_unet_eps(aldm_engine* e, const float* x, int64_t t, float* eps_uncond, float* eps_cond, void* stream);
+/* x_prev (and pred_x0 unless NULL) [B, C, T, F]; scalars as in aldm_ddim_step */
+int aldm_engine_ddim_step(aldm_engine* e, const float* x, int64_t t, const float* noise, float a_t, float a_prev,
+                          float sigma_t, float sqrt_one_minus_at, float guidance, float* x_prev, float* pred_x0,
+                          void* stream);
+int aldm_engine_vae_decode(aldm_engine* e, const float* z, float* mel, void* stream);
+int aldm_engine_vocoder(aldm_engine* e, const float* mel, float* wave, void* stream);
+int aldm_engine_vae_encode(aldm_engine* e, const float* mel, float* moments, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------- */
 
 int aldm_abi_version(void);
 size_t aldm_sizeof_op(void);
 size_t aldm_sizeof_gemm_desc(void);
+size_t aldm_sizeof_engine_desc(void);
 size_t aldm_offsetof_gemm(int32_t field);     /* 0:B 1:ntaps 2:dy 3:N 4:ldo 5:act 6:alpha 7:n_split (layout self-check) */
 const char* aldm_last_error(void);
 int aldm_device_check(int32_t device);

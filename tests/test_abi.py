@@ -62,6 +62,25 @@ def test_errors_are_codes_not_crashes(L):
     assert b"bn=48" in L.aldm_last_error()
 
 
+def test_engine_abi_validates_without_gpu(L):
+    """aldm_engine_* (SURVEY 8b seams): descriptor mirror + argument checks return codes, never crash."""
+    assert L.aldm_sizeof_engine_desc() == C.sizeof(_lib.EngineDesc)
+    h = C.c_void_p()
+    assert L.aldm_engine_create(None, C.byref(h)) == -1
+    d = _lib.EngineDesc()
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -1          # no UNet program / slots
+    assert b"UNet" in L.aldm_last_error()
+    d.unet_step, d.x_slot, d.t_slot, d.eps_slot = 1, 16, 16, 16           # dummy non-null handles: shape checks come next
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -2            # ALDM_E_SHAPE: B = 0
+    d.B, d.latent_elems, d.n_ctx = 2, 64, 1
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -1            # context 0 slots missing
+    d.n_ctx = 0
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == 0 and h.value
+    assert L.aldm_engine_vae_decode(h, None, None, None) == -1           # no decoder program
+    assert L.aldm_engine_set_conditioning(h, 2, None, None, 0, None, None, 0, None, None) == -1
+    L.aldm_engine_destroy(h)
+
+
 def test_product_path_does_not_import_oracle():
     pkg = os.path.join(ROOT, "audioldm2_b200")
     for fn in os.listdir(pkg):
