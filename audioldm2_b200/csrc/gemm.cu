@@ -546,7 +546,9 @@ struct Tc3Divs {
 
 template <int BN>
 struct Tc3Cfg : TcCfg<BN> {
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  // BN = 256 (planner switch ALDM_BN256, EXPERIMENTAL / not yet validated on hardware): 96 KB stages, two of them --
+  // the same bytes in flight as 3 x 64 KB, with 25% fewer operand bytes per FLOP and half the A-gather work.
+  static constexpr int STAGES = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);
   static constexpr int STG_BYTES = 8 * 32 * 33 * 4;     // one 32x33 fp32 transpose tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * TcCfg<BN>::STAGE_BYTES + 1024 + 256 + STG_BYTES;
 };
@@ -795,9 +797,10 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
       CoRows32 cr32;
       if (kCompact) cr32 = co_rows32(r, lane); else cr = co_rows(r, lane);
       // compact epilogues: bias and the first chunk's residual are fetched while the tile is still being accumulated
-      constexpr int NCH = BN > 64 ? 2 : 1;
+      constexpr int NCH = (BN + 63) / 64;       // 32-column chunks per epilogue warp
+      constexpr int NRV = NCH > 1 ? 2 : 1;      // residual prefetch buffers (rotating)
       uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);
-      float4 pb4[NCH], prv[NCH][8];
+      float4 pb4[NCH], prv[NRV][8];
       const bool has_res = kCompact && d.res != nullptr;
       if (kCompact && d.splitk == 1) {
 #pragma unroll
@@ -870,8 +873,8 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
             tmem_ld_wait();
             stage_rows(stg8, lane, reinterpret_cast<const float*>(vr));
             // the next chunk's residual is in flight while this one is written out
-            if (ch + 1 < NCH && has_res && c0 + 64 < BN) co_load_res32(d, cr32, n0 + 64, d.N, lane, prv[(ch + 1) % NCH]);
-            emit_rows<EPI == EPI_PLN>(d, cr32, n0, d.N, stg8, lane, prv[ch], has_res, pb4[ch]);
+            if (ch + 1 < NCH && has_res && c0 + 64 < BN) co_load_res32(d, cr32, n0 + 64, d.N, lane, prv[(ch + 1) % NRV]);
+            emit_rows<EPI == EPI_PLN>(d, cr32, n0, d.N, stg8, lane, prv[ch % NRV], has_res, pb4[ch]);
           }
         }
       } else if (EPI == EPI_FAST) {
@@ -1183,7 +1186,8 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
   const long long Mll = (long long)d.B * d.OH * d.OW;
   ALDM_REQUIRE(Mll > 0 && Mll < (1ll << 31), ALDM_E_SHAPE, "gemm: bad M=%lld", Mll);
   const int M = (int)Mll;
-  ALDM_REQUIRE(d.bn == 32 || d.bn == 64 || d.bn == 128, ALDM_E_UNSUPPORTED, "gemm: bn=%d unsupported", d.bn);
+  ALDM_REQUIRE(d.bn == 32 || d.bn == 64 || d.bn == 128 || (d.bn == 256 && (d.impl & 0xff) != ALDM_GEMM_TC_V1), ALDM_E_UNSUPPORTED,
+               "gemm: bn=%d unsupported", d.bn);
   ALDM_REQUIRE(d.Cp % 8 == 0 && d.Cp > 0, ALDM_E_SHAPE, "gemm: Cp=%d must be a positive multiple of 8", d.Cp);
   ALDM_REQUIRE(d.ntaps >= 1 && d.ntaps <= ALDM_MAX_TAPS, ALDM_E_SHAPE, "gemm: ntaps=%d", d.ntaps);
   ALDM_REQUIRE(d.K == d.ntaps * d.Cp, ALDM_E_SHAPE, "gemm: K=%d != ntaps*Cp=%d", d.K, d.ntaps * d.Cp);
@@ -1229,6 +1233,7 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
     }
   }
   switch (d.bn) {
+    case 256: return launch_tc2<256>(d, M, st);
     case 128: return launch_tc2<128>(d, M, st);
     case 64: return launch_tc2<64>(d, M, st);
     default: return launch_tc2<32>(d, M, st);

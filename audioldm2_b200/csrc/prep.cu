@@ -8,6 +8,8 @@
 //   LN  : ln_kernel        (one warp per token row, two-pass statistics in registers)
 //   misc: ew_kernel        (copy / SiLU / leaky-ReLU, optional concat of two sources, NCHW source)
 //         pack_b_kernel    (fp32 matrix -> swizzled hi/lo weight tile images, for dynamic B operands)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aldm {
@@ -290,8 +292,87 @@ __global__ void gn_apply_col_kernel(const __grid_constant__ aldm_prep_desc d, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL (off unless ALDM_GN_FUSED=1; not yet validated on hardware): statistics and
+// apply in ONE launch.  A block owns G consecutive groups of one sample, walks its [HW x G*cpg] slice twice
+// (second pass out of L2) and needs no scratch round trip.  Motivation: the step's launch list has 186
+// GroupNorm launches of 12-15 us for tensors of a few MB; at the 64..1024-pixel levels both kernels are
+// launch-latency-bound.  Thread mapping: tid -> (row lane, channel quad) with the quad fixed per thread, so a
+// thread accumulates for exactly one group.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_fused_kernel(const __grid_constant__ aldm_prep_desc d, int G) {
+  pdl_wait();
+  __shared__ double s_sum[8], s_sq[8];
+  __shared__ float s_mean[8], s_rstd[8];
+  const int b = blockIdx.y;
+  const int C = d.c0 + d.c1, cpg = C / d.groups, qpg = cpg >> 2;
+  const int qn = G * qpg;                       // channel quads per row owned by this block
+  const int c_base = blockIdx.x * G * cpg;
+  const int R = blockDim.x / qn;                // row lanes
+  const int rl = threadIdx.x / qn, q = threadIdx.x - rl * qn;
+  const bool active = rl < R;
+  if (threadIdx.x < 8) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int c = c_base + q * 4;
+  if (active) {
+    float a = 0.f, a2 = 0.f;
+    for (int r = rl; r < d.HW; r += R) {
+      const float4 v = load_cat4(d, (long long)b * d.HW + r, c);
+      a += (v.x + v.y) + (v.z + v.w);
+      a2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, a2))));
+    }
+    atomicAdd(&s_sum[q / qpg], (double)a);
+    atomicAdd(&s_sq[q / qpg], (double)a2);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const double n = (double)d.HW * cpg;
+    const double mean = s_sum[threadIdx.x] / n;
+    double var = s_sq[threadIdx.x] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)d.eps));
+  }
+  __syncthreads();
+  if (active) {
+    const float4 ga = *reinterpret_cast<const float4*>(d.gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(d.beta + c);
+    const float rs = s_rstd[q / qpg], mu = s_mean[q / qpg];
+    const float sc[4] = {rs * ga.x, rs * ga.y, rs * ga.z, rs * ga.w};
+    const float sh[4] = {be.x - mu * sc[0], be.y - mu * sc[1], be.z - mu * sc[2], be.w - mu * sc[3]};
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
+    __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+    const bool act = d.mode == ALDM_PREP_GN_SILU;
+    for (int r = rl; r < d.HW; r += R) {
+      const long long row = (long long)b * d.HW + r;
+      const float4 v = load_cat4(d, row, c);
+      float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+      if (act) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) y[e] = silu_f(y[e]);
+      }
+      store_planes4(hi + row * d.Cp + c, lo + row * d.Cp + c, y);
+    }
+  }
+  pdl_launch();
+}
+
+static bool gn_fused_enabled() {
+  static const bool on = [] { const char* e = getenv("ALDM_GN_FUSED"); return e && e[0] == '1'; }();
+  return on;
+}
+// groups per block of the fused kernel, or 0 if the shape is not eligible
+static int gn_fused_groups(const aldm_prep_desc& d) {
+  const int C = d.c0 + d.c1, cpg = C / d.groups;
+  if (!gn_fused_enabled() || cpg % 4 != 0 || d.HW > 4096) return 0;
+  int G = d.HW <= 1024 ? 4 : 2;
+  while (G > 1 && (d.groups % G != 0 || G * (cpg / 4) > 256)) G >>= 1;
+  return (G * (cpg / 4) <= 256 && G <= 8) ? G : 0;
+}
+
 int prep_num_launches(const aldm_prep_desc& d) {
-  return (d.mode == ALDM_PREP_GN || d.mode == ALDM_PREP_GN_SILU) ? 2 : 1;
+  if (d.mode != ALDM_PREP_GN && d.mode != ALDM_PREP_GN_SILU) return 1;
+  return (d.groups > 0 && (d.c0 + d.c1) % d.groups == 0 && gn_fused_groups(d)) ? 1 : 2;
 }
 
 int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
@@ -307,7 +388,10 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
     ALDM_REQUIRE(d.rows == d.B * d.HW, ALDM_E_SHAPE, "prep GN: rows != B*HW");
     ALDM_REQUIRE(!d.src_nchw, ALDM_E_UNSUPPORTED, "prep GN: NCHW source");
     const int cpg = C / d.groups;
-    if (cpg % 4 == 0) {
+    if (const int G = gn_fused_groups(d)) {
+      ALDM_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(d.groups / G, d.B), dim3(256), 0, st, d, G));
+      ALDM_CHECK_CUDA(cudaGetLastError());
+    } else if (cpg % 4 == 0) {
       // column-owner kernels: ~8 rows per block so that even the 64-pixel level fills the machine
       int nblk = cdiv(d.HW, 8);
       if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;

@@ -231,6 +231,8 @@ class Planner:
         self.keep_plain = keep_plain or impl == "simt"
         self.use_splitk = splitk and impl != "simt"
         self.static_b = os.environ.get("ALDM_BPRE", "1") != "0"      # weight prefetch ahead of the PDL wait (A/B switch)
+        # EXPERIMENTAL 128 x 256 tiles for N % 256 == 0 (csrc/gemm.cu Tc3Cfg<256>); off until validated on hardware
+        self.bn256 = os.environ.get("ALDM_BN256", "0") == "1" and impl == "tc"
         self.n_sm = n_sm
         self.arena = Arena()
         self.pool = Pool()
@@ -251,6 +253,8 @@ class Planner:
         yields >= ~0.8 * n_sm tiles (per-tile time of a short K loop is dominated by fixed latencies, so
         more, narrower tiles in flight win)."""
         cands = [b for b in ((128, 64) if geglu else (128, 64, 32)) if N % b == 0 and b >= min_bn]
+        if self.bn256 and N % 256 == 0:
+            cands = [256] + cands
         if not cands:
             return 128 if geglu else packing.choose_bn(N)
         if not m_rows:
@@ -283,9 +287,8 @@ class Planner:
         return WMat(Ref("w", self.arena.add(packed)), Ref("w", self.arena.add(plain)) if self.keep_plain else None,
                     bref, N, K, Kpad, bn, cp, ntaps)
 
-    @staticmethod
-    def bn_for_split(N: int, n_split: int) -> int:
-        for b in (128, 64, 32):
+    def bn_for_split(self, N: int, n_split: int) -> int:
+        for b in ((256,) if self.bn256 else ()) + (128, 64, 32):
             if n_split % b == 0 and N % b == 0:
                 return b
         raise ValueError((N, n_split))

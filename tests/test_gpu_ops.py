@@ -8,6 +8,8 @@ import ctypes as C
 import math
 
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -175,6 +177,13 @@ GEMM_CASES = {
     "nobias": dict(B=1, H=130, W=1, Cin=96, N=288, taps=((0, 0),), bias=False),
     "dual_out": dict(B=1, H=300, W=1, Cin=128, N=256, taps=((0, 0),), res=True, dual=True),
 }
+if os.environ.get("ALDM_BN256") == "1":      # extra shapes for the experimental 128 x 256 tile (scripts/gpu_experiments.sh)
+    GEMM_CASES.update({
+        "bn256_linear_res": dict(B=1, H=700, W=1, Cin=256, N=512, taps=((0, 0),), res=True),
+        "bn256_conv_rowvec": dict(B=2, H=24, W=8, Cin=64, N=256, taps=plan.TAPS_3x3, rowvec=True, res=True),
+        "bn256_planes": dict(B=1, H=260, W=1, Cin=128, N=256, taps=((0, 0),), out_kind="planes"),
+        "bn256_splitk": dict(B=2, H=8, W=2, Cin=256, N=256, taps=plan.TAPS_3x3, res=True),
+    })
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc", "tc1"])

@@ -31,6 +31,43 @@ def test_pack_roundtrip_and_swizzle():
         assert torch.equal(hi[off:off + 8], want)
 
 
+def test_bn256_tiles_plan(monkeypatch):
+    """EXPERIMENTAL 128 x 256 tiles (ALDM_BN256=1): packing, GEGLU row order and QKV split stay consistent with the
+    emulator's reading of the packed image (the kernel side is validated on hardware by scripts/gpu_experiments.sh)."""
+    import math
+    from audioldm2_b200 import _lib
+    from audioldm2_b200.plan import F32, Planner
+    monkeypatch.setenv("ALDM_BN256", "1")
+    g = torch.Generator().manual_seed(3)
+    M, K, N = 200, 96, 512
+    x = torch.randn(M, K, generator=g)
+    for geglu in (False, True):
+        P = Planner()
+        assert P.bn256
+        src = F32(P.raw(M * K * 4), M, K)
+        a = P.prep(_lib.PREP_COPY, src)
+        wm = torch.randn(N, K, generator=g) / math.sqrt(K)
+        bias = torch.randn(N, generator=g)
+        w = P.wmat(wm, bias, 1, K, geglu=geglu)
+        assert w.bn == 256
+        if geglu:
+            out = P.planes(M, N // 2)
+            P.gemm(a, w, B=1, H=M, out_planes=out, act=_lib.ACT_GEGLU)
+            y = x @ wm.t() + bias
+            want = y[:, :N // 2] * torch.nn.functional.gelu(y[:, N // 2:])
+        else:
+            o = P.f32(M, N)
+            P.gemm(a, w, B=1, H=M, out=o)
+            want = x @ wm.t() + bias
+        pl = P.finish(dict(src=("f32", src.ref, (M, K))))
+        em = Emulator(pl)
+        em.write_io("src", x)
+        em.run()
+        got = em.read_planes(out.hi, out.lo, M, out.Cp) if geglu else em.f32(o.ref, M * N).reshape(M, N)
+        assert rel_l2(got, want) < 2e-5
+    assert Planner().bn_for_split(768, 512) == 256
+
+
 def test_geglu_row_order():
     o = packing.geglu_row_order(256, 128)
     assert o.shape[0] == 512 and sorted(o.tolist()) == list(range(512))
