@@ -201,6 +201,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// 2-D tiled tensor-map load (TMA): box lands in shared memory in the map's swizzle mode; completes on `mbar` (tx bytes)
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tensor_map, int c0, int c1, uint32_t mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tensor_map)), "r"(mbar), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

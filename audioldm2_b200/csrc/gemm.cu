@@ -16,6 +16,9 @@
 //   warp 4     B producer: one elected lane issues a TMA bulk copy (cp.async.bulk) of the
 //              host-packed, pre-swizzled weight tile image (hi|lo) per stage.
 //   warp 5     allocates TMEM; one elected lane issues tcgen05.mma and commits stages.
+#ifdef ALDM_EXPERIMENTAL_TMA
+#include <cuda.h>
+#endif
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -553,9 +556,25 @@ struct Tc3Cfg : TcCfg<BN> {
   static constexpr int SMEM_BYTES = STAGES * TcCfg<BN>::STAGE_BYTES + 1024 + 256 + STG_BYTES;
 };
 
+// TMA = true (EXPERIMENTAL, ALDM_TMA_A=1, not yet validated on hardware): linear layers fetch the A tile with two
+// cp.async.bulk.tensor loads per stage (hi and lo plane; 2-D tensor maps over [rows, Cp] bf16 with 128-byte swizzle and
+// zero fill past the last row / channel) issued by ONE thread, instead of 128 threads x 16 cp.async each.  The maps ride
+// in a trailing kernel parameter that the TMA = false instantiations ignore (their code is unchanged by it).
+// Compiled in only with -DALDM_EXPERIMENTAL_TMA (ALDM_BUILD_EXPERIMENTAL=1 at build time): the default library keeps the
+// validated kernel signature and launch code byte for byte.
+#ifdef ALDM_EXPERIMENTAL_TMA
+struct TmaMaps { CUtensorMap hi, lo; };
+
+template <int BN, int EPI, bool TMA = false>
+__global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n,
+                                                           const __grid_constant__ Tc3Divs fd,
+                                                           const __grid_constant__ TmaMaps tm) {
+#else
 template <int BN, int EPI>
 __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n,
                                                            const __grid_constant__ Tc3Divs fd) {
+  constexpr bool TMA = false;
+#endif
   using C = Tc3Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -578,7 +597,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 128 + 1);   // 128 cp.async producers (completion-triggered arrivals) + B expect_tx
+      mbar_init(full_bar(s), TMA ? 2 : 128 + 1);   // 128 cp.async producers (completion-triggered arrivals) + B expect_tx; TMA: A issuer + B
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -612,6 +631,28 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     fd.tn.divmod(r, mt, nt);
   };
 
+#ifdef ALDM_EXPERIMENTAL_TMA
+  if (TMA && warp < 4) {
+    // ===================== A by TMA: one thread, two tensor loads per stage =====================
+    if (tid == 0) {
+      pdl_wait();
+      uint32_t cnt = 0;
+      for (int id = blockIdx.x; id < total; id += gridDim.x) {
+        int mt, nt, z, kb0, nkb;
+        tile_coords(id, mt, nt, z, kb0, nkb);
+        for (int it = 0; it < nkb; ++it, ++cnt) {
+          const int s = cnt % C::STAGES;
+          mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
+          const uint32_t sa = base + s * C::STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(s), 2 * C::A_BYTES);
+          tma_load_2d(sa, &tm.hi, (kb0 + it) * C::BK, mt * C::BM, full_bar(s));
+          tma_load_2d(sa + C::A_BYTES, &tm.lo, (kb0 + it) * C::BK, mt * C::BM, full_bar(s));
+        }
+      }
+    }
+    __syncwarp();
+  } else
+#endif
   if (warp < 4) {
     // ===================== A producers =====================
     const int j = tid & 7;                 // 16-byte chunk (8 channels) inside the 64-wide K block
@@ -1116,6 +1157,38 @@ static int launch_tc(const aldm_gemm_desc& d, int M, cudaStream_t st) {
 
 static int g_num_sms = 0;
 
+#ifdef ALDM_EXPERIMENTAL_TMA
+// ---- tensor maps for the experimental TMA A path (driver entry point fetched at run time: no libcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+static bool tma_a_enabled() {
+  static const bool on = [] { const char* e = getenv("ALDM_TMA_A"); return e && e[0] == '1' && encode_tiled_fn() != nullptr; }();
+  return on;
+}
+// [rows, Cp] bf16 plane, box = 64 channels x 128 rows, 128-byte swizzle (the layout the UMMA descriptors expect), zero OOB fill
+static bool make_plane_map(CUtensorMap* tm, const void* base, int rows, int Cp) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)Cp, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Cp * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t es[2] = {1, 1};
+  return encode_tiled_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+#endif
+
 template <int BN, int EPI>
 static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   using C = Tc3Cfg<BN>;
@@ -1137,7 +1210,29 @@ static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   fd.bmod = make_fastdiv(d.bmod > 0 ? d.bmod : 1);
   fd.plain = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.sy == 1 && d.sx == 1 && d.up == 0 && d.bmod <= 0 &&
              d.OH == d.H && d.OW == d.W;
+#ifdef ALDM_EXPERIMENTAL_TMA
+  static TmaMaps no_maps = {};
+  bool launched = false;
+  if constexpr ((EPI == EPI_GEGLU || EPI == EPI_F32N || EPI == EPI_PLN) && BN >= 128) {
+    // EXPERIMENTAL (ALDM_TMA_A=1): linear layers with at least one full K block per row take the tensor-map A path
+    if (tma_a_enabled() && fd.plain && d.Cp >= 64 && aligned16(d.a_hi) && aligned16(d.a_lo)) {
+      static bool configured_tma = false;
+      if (!configured_tma) {
+        ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured_tma = true;
+      }
+      TmaMaps maps;
+      ALDM_REQUIRE(make_plane_map(&maps.hi, d.a_hi, M, d.Cp) && make_plane_map(&maps.lo, d.a_lo, M, d.Cp), ALDM_E_CUDA,
+                   "gemm: cuTensorMapEncodeTiled failed (rows=%d Cp=%d)", M, d.Cp);
+      ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI, true>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd, maps));
+      launched = true;
+    }
+  }
+  if (!launched)
+    ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI, false>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd, no_maps));
+#else
   ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd));
+#endif
   ALDM_CHECK_CUDA(cudaGetLastError());
   if (d.splitk > 1) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
