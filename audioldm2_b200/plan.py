@@ -253,7 +253,7 @@ class Planner:
         yields >= ~0.8 * n_sm tiles (per-tile time of a short K loop is dominated by fixed latencies, so
         more, narrower tiles in flight win)."""
         cands = [b for b in ((128, 64) if geglu else (128, 64, 32)) if N % b == 0 and b >= min_bn]
-        if self.bn256 and N % 256 == 0:
+        if self.bn256 and N % 256 == 0 and self._bn256_pays(N, m_rows):
             cands = [256] + cands
         if not cands:
             return 128 if geglu else packing.choose_bn(N)
@@ -265,6 +265,17 @@ class Planner:
                 return b
         return cands[-1]
 
+    def _bn256_pays(self, N: int, m_rows: Optional[int]) -> bool:
+        """128 x 256 tiles halve the tile count: take them only when that still fills the persistent grid at least
+        (nearly) once and does not lose more than a few percent to wave quantisation against 128 x 128 tiles
+        (e.g. M = 1024, N = 5120: 160 tiles on 148 SMs would run two rounds at 54% -- keep 128 there)."""
+        if not m_rows:
+            return True
+        mt = math.ceil(m_rows / 128)
+        eff = lambda tiles: tiles / (math.ceil(tiles / self.n_sm) * self.n_sm)
+        t256, t128 = mt * (N // 256), mt * (N // 128)
+        return t256 >= int(0.8 * self.n_sm) and eff(t256) >= eff(t128) - 0.03
+
     def wmat(self, wm: torch.Tensor, bias: Optional[torch.Tensor], ntaps: int, cp: int, geglu: bool = False,
              bn: Optional[int] = None, m_rows: Optional[int] = None) -> WMat:
         N, K = wm.shape
@@ -273,6 +284,8 @@ class Planner:
         # (more CTAs re-read the same activation rows, MMA N=32/64 is less efficient), so the widest tile
         # that divides N is always used; m_rows is kept for future tuning.
         narrow = int(os.environ.get("ALDM_NARROW", "0"))       # experiment switch: smallest N tile the heuristic may pick
+        if bn is None and self.bn256 and N % 256 == 0 and not narrow:
+            bn = 256 if self._bn256_pays(N, m_rows) else None
         bn = bn or self.bn_for_rows(N, m_rows if narrow else None, geglu, min_bn=narrow or 32)
         if geglu:
             order = packing.geglu_row_order(N // 2, bn)
