@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
 MAX_TAPS = 16
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # enums (keep in sync with the header; checked by tests/test_abi.py against the header text)
 GEMM_TC, GEMM_SIMT, GEMM_TC_V1 = 0, 1, 2
@@ -106,11 +106,20 @@ class Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("tag", C.c_int32), ("u", _OpU)]
 
 
+MAX_LANES = 8
+
+
+class UnetLane(C.Structure):
+    """aldm_unet_lane: one independent sub-batch of the UNet (own programs + workspace slots)."""
+    _fields_ = [("cond", C.c_void_p), ("step", C.c_void_p), ("x_slot", C.c_void_p), ("t_slot", C.c_void_p),
+                ("eps_slot", C.c_void_p), ("ctx_slot", C.c_void_p * 2), ("mask_slot", C.c_void_p * 2),
+                ("film_slot", C.c_void_p)]
+
+
 class EngineDesc(C.Structure):
     """aldm_engine_desc (include/aldm_b200.h): programs + their fixed I/O slots."""
-    _fields_ = [("unet_cond", C.c_void_p), ("unet_step", C.c_void_p), ("vae_dec", C.c_void_p), ("vocoder", C.c_void_p),
-                ("vae_enc", C.c_void_p), ("x_slot", C.c_void_p), ("t_slot", C.c_void_p), ("eps_slot", C.c_void_p),
-                ("ctx_slot", C.c_void_p * 2), ("mask_slot", C.c_void_p * 2), ("film_slot", C.c_void_p),
+    _fields_ = [("lane", UnetLane * MAX_LANES), ("n_lanes", C.c_int32),
+                ("vae_dec", C.c_void_p), ("vocoder", C.c_void_p), ("vae_enc", C.c_void_p),
                 ("z_slot", C.c_void_p), ("mel_slot", C.c_void_p), ("voc_mel_slot", C.c_void_p), ("wave_slot", C.c_void_p),
                 ("enc_mel_slot", C.c_void_p), ("moments_slot", C.c_void_p), ("B", C.c_int32), ("latent_elems", C.c_int32),
                 ("mel_elems", C.c_int32), ("wave_len", C.c_int32), ("n_ctx", C.c_int32), ("ctx_len", C.c_int32 * 2),

@@ -30,6 +30,43 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class ShardedNoise:
+    """SURVEY.md 8e seeding rule: an N-rank run must produce the rows the single-process batch would.  Every rank draws
+    the FULL-batch tensors (x_T, then per DDIM step the q_sample noise when masked and the step noise, in the reference's
+    order, ddim.py:191,351 / ddpm.py:431) from the same seed with the same generator and keeps rows [lo, hi) -- 131 KB per
+    sample and draw, no communication.  Use as ``x_T=sn.x_T(), noise_fn=sn`` of ``generate_latent``."""
+
+    def __init__(self, global_batch: int, lo: int, hi: int, latent, device, seed: int = 42, generator=None):
+        self.shape = (int(global_batch),) + tuple(int(v) for v in latent)
+        self.lo, self.hi, self.device = lo, hi, torch.device(device)
+        if generator is None:
+            generator = torch.Generator(device=self.device)
+            generator.manual_seed(int(seed))
+        self.gen = generator
+
+    def _draw(self) -> torch.Tensor:
+        return torch.randn(self.shape, device=self.device, generator=self.gen)[self.lo:self.hi].contiguous()
+
+    def x_T(self) -> torch.Tensor:
+        return self._draw()
+
+    def __call__(self, i: int, kind: str) -> torch.Tensor:
+        return self._draw()
+
+
+def shard_rows(t, lo: int, hi: int):
+    """Rows [lo, hi) of every tensor in a (nested) conditioning structure."""
+    if t is None:
+        return None
+    if torch.is_tensor(t):
+        return t[lo:hi].contiguous()
+    if isinstance(t, dict):
+        return {k: shard_rows(v, lo, hi) for k, v in t.items()}
+    if isinstance(t, (list, tuple)):
+        return [shard_rows(v, lo, hi) for v in t]
+    return t
+
+
 def make_arena_bcast(device, src: int = 0):
     """Hook for NativeLatentDiffusion(arena_bcast=...): rank ``src`` uploads its packed arena, every
     other rank receives it over NCCL (NVLink/NVSwitch) instead of packing + uploading its own."""

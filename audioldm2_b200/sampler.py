@@ -76,7 +76,11 @@ class DDIMSampler:
         m = self.model
         dev = m.device
         img = torch.randn(shape, device=dev) if x_T is None else x_T.to(dev).contiguous().clone()   # ddim.py:191
-        m.set_conditioning(cond, unconditional_conditioning)
+        # ddim.py:293-296: without an unconditional branch (or with scale 1.0) the model output is apply_model(x, t, c)
+        # alone.  The engine always evaluates two halves, so the conditional branch is loaded into both: e_u == e_c
+        # bit for bit (same kernels, same data) and e_u + s (e_c - e_u) == e_c exactly.
+        single = unconditional_conditioning is None or unconditional_guidance_scale == 1.0
+        m.set_conditioning(cond, None if single else unconditional_conditioning)
         nxt = torch.empty_like(img)
         for i, st in enumerate(self.steps):
             if mask is not None:                                                   # ddim.py:226-231

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define ALDM_ABI_VERSION 5
+#define ALDM_ABI_VERSION 6
 #define ALDM_MAX_TAPS 16
 
 enum {
@@ -247,30 +247,43 @@ void aldm_program_destroy(aldm_program* p);
  *   aldm_engine_vae_decode        <- LatentDiffusion.decode_first_stage (ddpm.py:922-926)
  *   aldm_engine_vocoder           <- first_stage_model.vocoder(mel) in mel_spectrogram_to_waveform (ddpm.py:928-939)
  *   aldm_engine_vae_encode        <- encode_first_stage (ddpm.py:941-943), moments out
- * The engine borrows the programs (it never destroys them) and owns nothing but its descriptor copy.  All
+ * The engine borrows the programs (it never destroys them) and owns its descriptor copy plus the step graph
+ * (all lanes as parallel branches) and the side streams / events used to capture it.  All
  * pointers are device pointers, fp32 contiguous NCHW as in the reference; everything is enqueued on `stream`;
  * nothing synchronises.  Single caller thread per engine. */
 typedef struct aldm_engine aldm_engine;
 
+#define ALDM_MAX_LANES 8
+
+/* One UNet lane: an independent copy of the step / conditioning programs planned for B / n_lanes latent rows, with
+ * its own workspace (the weight arena is shared).  Lanes are replayed as PARALLEL branches of one CUDA graph: the
+ * UNet's deep levels are chains of ~10 us kernels that each fill a fraction of the 148 SMs, so independent
+ * sub-batches overlap there while the large layers simply share the machine.  Samples are independent through the
+ * whole path, so results do not depend on the lane count (up to split-K / tile-shape choices). */
+typedef struct aldm_unet_lane {
+  aldm_program* cond;           /* cross-attention K/V precompute (may be NULL: no cross-attention) */
+  aldm_program* step;           /* one UNet evaluation of 2*Bl rows: rows [0,Bl) unconditional, [Bl,2Bl) conditional */
+  float* x_slot;                /* [Bl, C, T, F] latent read by `step` */
+  int64_t* t_slot;              /* [2Bl] DDPM timestep */
+  float* eps_slot;              /* [2Bl, C, T, F] */
+  float* ctx_slot[2];           /* [2Bl, ctx_len[i], ctx_dim[i]] zero-padded context i */
+  float* mask_slot[2];          /* [2Bl, ctx_len[i]] 1 = attend */
+  float* film_slot;             /* [2Bl, film_dim] or NULL */
+} aldm_unet_lane;
+
 typedef struct aldm_engine_desc {
-  aldm_program* unet_cond;      /* cross-attention K/V precompute (may be NULL: no cross-attention) */
-  aldm_program* unet_step;      /* one UNet evaluation of 2*B rows: rows [0,B) unconditional, [B,2B) conditional */
+  aldm_unet_lane lane[ALDM_MAX_LANES];   /* lane l owns latent rows [l*B/n_lanes, (l+1)*B/n_lanes) */
+  int32_t n_lanes;              /* 1..ALDM_MAX_LANES, B % n_lanes == 0 */
   aldm_program* vae_dec;        /* may be NULL */
   aldm_program* vocoder;        /* may be NULL */
   aldm_program* vae_enc;        /* may be NULL */
-  float* x_slot;                /* [B, C, T, F] latent read by unet_step */
-  int64_t* t_slot;              /* [2B] DDPM timestep */
-  float* eps_slot;              /* [2B, C, T, F] */
-  float* ctx_slot[2];           /* [2B, ctx_len[i], ctx_dim[i]] zero-padded context i */
-  float* mask_slot[2];          /* [2B, ctx_len[i]] 1 = attend */
-  float* film_slot;             /* [2B, film_dim] or NULL */
   float* z_slot;                /* vae_dec input [B, C, T, F] */
   float* mel_slot;              /* vae_dec output [B, 1, T', F'] */
   float* voc_mel_slot;          /* vocoder input [B, T', F'] */
   float* wave_slot;             /* vocoder output [B, 1, L] */
   float* enc_mel_slot;          /* vae_enc input [B, 1, T', F'] */
   float* moments_slot;          /* vae_enc output [B, T, F, 2C] (channels-last) */
-  int32_t B;                    /* latent batch the programs were planned for */
+  int32_t B;                    /* latent batch the programs were planned for (all lanes together) */
   int32_t latent_elems;         /* C*T*F */
   int32_t mel_elems;            /* T'*F' */
   int32_t wave_len;             /* L */
@@ -278,7 +291,7 @@ typedef struct aldm_engine_desc {
   int32_t ctx_len[2];
   int32_t ctx_dim[2];
   int32_t film_dim;
-  int32_t use_graph;            /* 1: unet_step is captured on first use and replayed */
+  int32_t use_graph;            /* 1: the lanes' step programs are captured into one graph on first use and replayed */
 } aldm_engine_desc;
 
 int aldm_engine_create(const aldm_engine_desc* d, aldm_engine** out);

@@ -68,12 +68,18 @@ def test_engine_abi_validates_without_gpu(L):
     h = C.c_void_p()
     assert L.aldm_engine_create(None, C.byref(h)) == -1
     d = _lib.EngineDesc()
-    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -1          # no UNet program / slots
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -1          # n_lanes = 0
+    assert b"n_lanes" in L.aldm_last_error()
+    d.n_lanes = 2
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -2          # ALDM_E_SHAPE: B = 0
+    d.B, d.latent_elems, d.n_ctx = 3, 64, 1
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -2          # B % n_lanes != 0
+    d.B = 2
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -1          # lane 0: no UNet program / slots
     assert b"UNet" in L.aldm_last_error()
-    d.unet_step, d.x_slot, d.t_slot, d.eps_slot = 1, 16, 16, 16           # dummy non-null handles: shape checks come next
-    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -2            # ALDM_E_SHAPE: B = 0
-    d.B, d.latent_elems, d.n_ctx = 2, 64, 1
-    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -1            # context 0 slots missing
+    for l in range(2):                                                   # dummy non-null handles
+        d.lane[l].step, d.lane[l].x_slot, d.lane[l].t_slot, d.lane[l].eps_slot = 1, 16, 16, 16
+    assert L.aldm_engine_create(C.byref(d), C.byref(h)) == -1          # context 0 slots missing
     d.n_ctx = 0
     assert L.aldm_engine_create(C.byref(d), C.byref(h)) == 0 and h.value
     assert L.aldm_engine_vae_decode(h, None, None, None) == -1           # no decoder program

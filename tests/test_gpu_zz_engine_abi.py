@@ -1,8 +1,7 @@
-"""Engine-level C-ABI (aldm_engine_*, include/aldm_b200.h): the reference's seams as single C calls.
-The same programs driven through it must reproduce the Python-orchestrated path bit for bit, and the
-reference fixture within the network tolerance."""
-import ctypes as C
-
+"""Engine-level C-ABI (aldm_engine_*, include/aldm_b200.h): the reference's seams as single C calls, and UNet lanes.
+The lane count (independent sub-batches replayed as parallel branches of one CUDA graph) must not change the
+result beyond tile-shape / split-K rounding, graph replay must equal the eager run, and everything must match
+the reference fixture within the network tolerance."""
 import pytest
 import torch
 
@@ -15,32 +14,50 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("use_graph", [True, False])
-def test_engine_abi_matches_python_host(use_graph):
+def test_engine_lanes_and_output_pointers(use_graph):
     cfg = arch.tiny_config()
     g = cases.load("ddim_tiny")
     _, _, cond, unc = cases.unet_inputs(cfg, 2, t5_len=5)
     x_T, noises, qn = cases.sampler_noise(cfg, 2, 5, masked=False)
     nf = lambda i, kind: noises[i].to(DEV)
     outs = []
-    for abi in (False, True):
-        eng = _engine(cfg, 2, 5, use_engine_abi=abi, use_graph=use_graph)
+    for lanes in (1, 2):
+        eng = _engine(cfg, 2, 5, lanes=lanes, use_graph=use_graph)
+        assert eng.lanes == lanes
         z = eng.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=5, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf)
         wav = eng.mel_spectrogram_to_waveform(eng.decode_first_stage(z)).clone()
         outs.append((z.clone(), wav))
-        if abi:
-            # explicit output pointers of aldm_engine_unet_eps / aldm_engine_vae_decode / aldm_engine_vocoder
-            L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
-            x = x_T.to(DEV).contiguous()
-            eu, ec = torch.empty_like(x), torch.empty_like(x)
-            _lib.check(L.aldm_engine_unet_eps(eng._engine, x.data_ptr(), 801, eu.data_ptr(), ec.data_ptr(), st))
-            e2u, e2c = eng.apply_model_pair(x, 801)
-            assert torch.equal(eu, e2u) and torch.equal(ec, e2c)
-            mel = torch.empty(2, 1, *eng.mel_hw, device=DEV)
-            _lib.check(L.aldm_engine_vae_decode(eng._engine, z.contiguous().data_ptr(), mel.data_ptr(), st))
-            w2 = torch.empty_like(wav)
-            _lib.check(L.aldm_engine_vocoder(eng._engine, mel.data_ptr(), w2.data_ptr(), st))
-            assert torch.equal(w2, wav)
+        # explicit output pointers of aldm_engine_unet_eps / aldm_engine_vae_decode / aldm_engine_vocoder
+        L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+        x = x_T.to(DEV).contiguous()
+        eu, ec = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(L.aldm_engine_unet_eps(eng._engine, x.data_ptr(), 801, eu.data_ptr(), ec.data_ptr(), st))
+        e2u, e2c = eng.apply_model_pair(x, 801)
+        assert torch.equal(eu, e2u) and torch.equal(ec, e2c)
+        mel = torch.empty(2, 1, *eng.mel_hw, device=DEV)
+        _lib.check(L.aldm_engine_vae_decode(eng._engine, z.contiguous().data_ptr(), mel.data_ptr(), st))
+        w2 = torch.empty_like(wav)
+        _lib.check(L.aldm_engine_vocoder(eng._engine, mel.data_ptr(), w2.data_ptr(), st))
+        assert torch.equal(w2, wav)
     (z0, w0), (z1, w1) = outs
-    assert torch.equal(z0, z1), f"latent differs: {rel_l2(z1, z0):.3e}"
-    assert torch.equal(w0, w1), f"waveform differs: {rel_l2(w1, w0):.3e}"
-    assert rel_l2(z1, g["latent"]) < 2e-4
+    assert rel_l2(z1, z0) < 2e-5, f"latent differs between 1 and 2 lanes: {rel_l2(z1, z0):.3e}"
+    assert rel_l2(w1, w0) < 2e-5, f"waveform differs between 1 and 2 lanes: {rel_l2(w1, w0):.3e}"
+    assert rel_l2(z1, g["latent"]) < 2e-4 and rel_l2(z0, g["latent"]) < 2e-4
+
+
+def test_conditional_only_and_keyed_cond_dict():
+    """ddim.py:293: no unconditional branch / scale 1.0 -> the model output is apply_model(x, t, c) alone; and the
+    reference's keyed cond-dict (DiffusionWrapper.forward, ddpm.py:1821-1879) is accepted as is."""
+    cfg = arch.tiny_config()
+    g = cases.load("unet_tiny")
+    x, t, cond, unc = cases.unet_inputs(cfg, 2, t5_len=5)
+    eng = _engine(cfg, 2, 5, conditioning_key=["crossattn_audiomae_generated", "crossattn_flan_t5"])
+    keyed = {"crossattn_flan_t5": [cond["context_list"][1].to(DEV), cond["mask_list"][1].to(DEV)],
+             "crossattn_audiomae_generated": [cond["context_list"][0].to(DEV), cond["mask_list"][0].to(DEV)]}
+    e = eng.apply_model(x.to(DEV), t.to(DEV), keyed)
+    assert rel_l2(e, g["eps_cond"]) < 1e-4
+    x_T, noises, _ = cases.sampler_noise(cfg, 2, 3)
+    nf = lambda i, kind: noises[i].to(DEV)
+    za = eng.generate_latent(keyed, None, ddim_steps=3, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf).clone()
+    zb = eng.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=3, guidance=1.0, eta=1.0, x_T=x_T, noise_fn=nf).clone()
+    assert torch.equal(za, zb)
