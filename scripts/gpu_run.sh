@@ -1,0 +1,41 @@
+#!/bin/bash
+# One parameterised GPU job runner (replaces the round-1 one-offs).  Usage (under gpurun, from the repo root):
+#   bash scripts/gpu_run.sh tests            # pytest -m gpu
+#   bash scripts/gpu_run.sh sweep            # ms / DDIM step for lanes x switches (scripts/step_time.py)
+#   bash scripts/gpu_run.sh bench [args...]  # python bench.py args -> gpurun_out/bench_<tag>.json
+#   bash scripts/gpu_run.sh ncu-list         # per-launch times of 2 eager DDIM steps (profiles/*_launches.md source)
+# Several jobs: bash scripts/gpu_run.sh tests sweep bench
+set +e
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TAG=${TAG:-r02}
+python __graft_entry__.py > gpurun_out/build_$TAG.log 2>&1 || { tail -20 gpurun_out/build_$TAG.log; exit 1; }
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader > gpurun_out/smi_$TAG.txt
+nproc > gpurun_out/nproc.txt
+while [ $# -gt 0 ]; do
+  job=$1; shift
+  case $job in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_$TAG.log 2>&1
+      echo "== tests rc=$?"; tail -5 gpurun_out/pytest_$TAG.log ;;
+    sweep)
+      : > gpurun_out/sweep_$TAG.jsonl
+      for cfg in "1:" "2:" "4:" "2:ALDM_GN_FUSED=1" "2:ALDM_BN256=1" "2:ALDM_GN_FUSED=1 ALDM_BN256=1" "4:ALDM_GN_FUSED=1"; do
+        lanes=${cfg%%:*}; sw=${cfg#*:}
+        env $sw timeout 300 python scripts/step_time.py --lanes $lanes --tag "lanes$lanes $sw" 2>gpurun_out/sweep_err.log | grep '^{' >> gpurun_out/sweep_$TAG.jsonl || tail -3 gpurun_out/sweep_err.log
+      done
+      echo "== sweep"; cat gpurun_out/sweep_$TAG.jsonl ;;
+    bench)
+      timeout 1500 python bench.py $BENCH_ARGS > gpurun_out/bench_$TAG.log 2>&1
+      echo "== bench rc=$?"; grep '^{"metric"' gpurun_out/bench_$TAG.log > gpurun_out/bench_$TAG.json; tail -c 1500 gpurun_out/bench_$TAG.log ;;
+    refarm)
+      timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1
+      echo "== reference arm rc=$?"; tail -c 1200 gpurun_out/bench_ref_$TAG.log ;;
+    ncu-list)
+      timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
+        --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 0 --ddim-steps 2 --no-graph --no-cpu-baseline \
+        --no-torch-cuda-baseline --no-kernel-pass $BENCH_ARGS > gpurun_out/ncu_list_$TAG.log 2>&1
+      echo "== ncu-list rc=$?"; tail -2 gpurun_out/ncu_list_$TAG.log ;;
+    *) echo "unknown job $job" ;;
+  esac
+done

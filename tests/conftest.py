@@ -24,3 +24,17 @@ def rel_l2(a, b):
 def have_cuda():
     import torch
     return torch.cuda.is_available()
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device and the built library: skip them cleanly elsewhere (a plain `pytest tests`
+    on the CPU build box then runs the CPU suite only)."""
+    import torch
+    lib = os.path.join(ROOT, "audioldm2_b200", "libaldm_b200.so")
+    if torch.cuda.is_available() and os.path.exists(lib):
+        return
+    why = "no CUDA device" if not torch.cuda.is_available() else "libaldm_b200.so not built"
+    skip = pytest.mark.skip(reason=f"gpu test: {why}")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
