@@ -2,16 +2,19 @@
 // the reference materialises it: attention.py:354-366).
 //
 // attention_tc_kernel (tcgen05): one CTA = 128 queries of one (batch, head); keys are streamed in
-// tiles of 64.  Operands are the bf16 hi/lo planes written by the projection GEMMs
-// (ALDM_OUT_QKV): Q, K row-major, V already transposed (keys contiguous), so every operand tile is
-// a plain cp.async copy into the same 128-byte-swizzled K-major layout the GEMM uses.
-//   S = Q K^T       : q_hi k_hi^T + q_hi k_lo^T + q_lo k_hi^T, 2 K-steps of 16 each      -> TMEM (6 UMMAs)
+// tiles of 64.  Operands are single fp16 planes (the hi planes written by the projection GEMMs,
+// ALDM_OUT_QKV): Q, K row-major, V already transposed (keys contiguous), so every operand tile is
+// a plain cp.async copy into the same 128-byte-swizzled K-major layout the GEMM uses.  Both operands of the
+// two products are activations; rounding them to 11 bits costs 1.2e-4 of the 1e-3 waveform budget at 10 DDIM
+// steps (scripts/precision_study.py --only attn), a third of the tensor work and half the bytes of the split form.
+//   S = Q K^T       : 2 K-steps of 16                                                   -> TMEM (2 UMMAs)
 //   softmax          : 128 threads, one query row each (TMEM lane == row), online max/sum in the
-//                      log2 domain, P split to bf16 hi/lo and written to shared memory as the A operand
-//   O_tile = P V     : 3 passes x 4 K-steps, N = 32                                    -> TMEM (12 UMMAs)
+//                      log2 domain, P rounded to fp16 and written to shared memory as the A operand
+//                      (the row sum is accumulated from the unrounded fp32 values)
+//   O_tile = P V     : 4 K-steps, N = 32                                                -> TMEM (4 UMMAs)
 //   O += rescaled O_tile in registers (no TMEM read-modify-write)
 // Warp roles: 0-3 softmax/epilogue, 4 loader (cp.async + mbarrier), 5 TMEM alloc + MMA issue.
-// ~97 KB shared memory and 128 TMEM columns per CTA -> two CTAs per SM overlap each other's MMA
+// ~81 KB shared memory and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's MMA
 // and softmax phases.
 //
 // attention_simt_kernel: CUDA-core checker on the same operands (validation only).
@@ -34,21 +37,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// one query row of one head -> output plane(s) (lo only when the consumer asked for a second plane)
+__device__ __forceinline__ void store_out_row(const aldm_attn_desc& d, long long orow, int h, const float* o) {
+  aldm_plane_t* hp = reinterpret_cast<aldm_plane_t*>(d.out_hi) + orow * d.ldo + h * ATT_D;
+  aldm_plane_t* lp = d.out_lo ? reinterpret_cast<aldm_plane_t*>(d.out_lo) + orow * d.ldo + h * ATT_D : nullptr;
+#pragma unroll
+  for (int i = 0; i < ATT_D; i += 8) {
+    uint4 hh, ll;
+    split8(o + i, hh, ll);
+    *reinterpret_cast<uint4*>(hp + i) = hh;
+    if (lp) *reinterpret_cast<uint4*>(lp + i) = ll;
+  }
+}
+
 namespace atc {
 constexpr int QT = 128, KT = 64;
-// NS = number of K/V stages.  The profile of the 2-stage kernel showed the softmax warps idle 43% of the time
-// waiting for S: a stage is only released after P V(it), so K(it+2) was requested one tile period before it was
-// needed, less than the L2 latency under load.  Three stages give two periods of prefetch distance.  They fit in
-// the same 97 KB (two CTAs per SM) because Q is stored once as [q_hi | q_lo] rows: every K=16 MMA step takes its
-// own descriptor, so the three product terms just use different 32-byte offsets inside the 128-byte swizzled rows
-// (an earlier layout kept a second [q_hi | q_hi] copy to pair with [k_hi | k_lo]).
+// NS = number of K/V stages (a stage is released after P V(it), so the prefetch distance is NS - 1 tile periods; the
+// 2-stage kernel of round 1 left the softmax warps waiting for S 43% of the time).  Rows are 128 bytes in the
+// SWIZZLE_128B layout; Q and K use the first 64 bytes of each row (32 dims x fp16), V^T and P all 128 (64 keys).
 template <int NS>
 struct Cfg {
-  static constexpr int QA = 0;                           // [128][128B]  q_hi | q_lo
-  static constexpr int KB = QA + QT * 128;               // NS x [64][128B]   k_hi | k_lo
-  static constexpr int VT = KB + NS * KT * 128;          // NS x {hi,lo} x [32][128B]
-  static constexpr int PP = VT + NS * 2 * ATT_D * 128;   // {hi,lo} x [128][128B]
-  static constexpr int BAR = PP + 2 * QT * 128;
+  static constexpr int QA = 0;                           // [128][128B]  q in chunks 0..3
+  static constexpr int KB = QA + QT * 128;               // NS x [64][128B]   k in chunks 0..3
+  static constexpr int VT = KB + NS * KT * 128;          // NS x [32][128B]   v^T (64 keys per row)
+  static constexpr int PP = VT + NS * ATT_D * 128;       // [128][128B]       p (64 keys per row)
+  static constexpr int BAR = PP + QT * 128;
   static constexpr int SMEM = BAR + 128 + 1024;          // + barriers + round-up slack for the 1024-byte tile alignment
 };
 constexpr int TMEM_COLS = 256;                 // S double buffer: cols [0,64) / [64,128); O_tile: cols [128,160)
@@ -155,13 +168,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       }
       uint8_t* ph = sm + PP + row * 128;
 #pragma unroll
-      for (int c = 0; c < KT / 8; ++c) {
-        uint4 hi, lo;
-        split8(s + c * 8, hi, lo);
-        const uint32_t off = ((uint32_t)c ^ swz) << 4;
-        *reinterpret_cast<uint4*>(ph + off) = hi;
-        *reinterpret_cast<uint4*>(ph + QT * 128 + off) = lo;
-      }
+      for (int c = 0; c < KT / 8; ++c) *reinterpret_cast<uint4*>(ph + (((uint32_t)c ^ swz) << 4)) = pack8_hi(s + c * 8);
       fence_proxy_async();          // P (generic-proxy stores) -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
@@ -181,57 +188,46 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       const float inv = 1.0f / lrun;
 #pragma unroll
       for (int i = 0; i < ATT_D; ++i) o[i] *= inv;
-      const long long orow = (long long)b * d.Nq + q;
-      __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + h * ATT_D;
-      __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + h * ATT_D;
-#pragma unroll
-      for (int i = 0; i < ATT_D; i += 8) {
-        uint4 hh, ll;
-        split8(o + i, hh, ll);
-        *reinterpret_cast<uint4*>(hp + i) = hh;
-        *reinterpret_cast<uint4*>(lp + i) = ll;
-      }
+      store_out_row(d, (long long)b * d.Nq + q, h, o);
     }
   } else if (warp == 4) {
     // =============================== loader ===============================
-    const __nv_bfloat16* qh = reinterpret_cast<const __nv_bfloat16*>(d.q_hi);
-    const __nv_bfloat16* ql = reinterpret_cast<const __nv_bfloat16*>(d.q_lo);
-    const __nv_bfloat16* kh = reinterpret_cast<const __nv_bfloat16*>(d.k_hi);
-    const __nv_bfloat16* kl = reinterpret_cast<const __nv_bfloat16*>(d.k_lo);
-    const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(d.vt_hi);
-    const __nv_bfloat16* vl = reinterpret_cast<const __nv_bfloat16*>(d.vt_lo);
-    // Q: row r chunk c <- (c < 4 ? q_hi : q_lo) chunk (c & 3)
-    for (int idx = lane; idx < QT * 8; idx += 32) {
-      const int r = idx >> 3, c = idx & 7;
+    const aldm_plane_t* qh = reinterpret_cast<const aldm_plane_t*>(d.q_hi);
+    const aldm_plane_t* kh = reinterpret_cast<const aldm_plane_t*>(d.k_hi);
+    const aldm_plane_t* vh = reinterpret_cast<const aldm_plane_t*>(d.vt_hi);
+    // Q: row r, chunks 0..3 (32 dims)
+    for (int idx = lane; idx < QT * 4; idx += 32) {
+      const int r = idx >> 2, c = idx & 3;
       const bool ok = q0 + r < d.Nq;
-      const long long off = ok ? ((long long)b * d.Nq + q0 + r) * d.ldq + d.q_col + h * ATT_D + (c & 3) * 8 : 0;
-      cp_async_16(base + QA + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), (c < 4 ? qh : ql) + off, ok ? 16u : 0u);
+      const long long off = ok ? ((long long)b * d.Nq + q0 + r) * d.ldq + d.q_col + h * ATT_D + c * 8 : 0;
+      cp_async_16(base + QA + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), qh + off, ok ? 16u : 0u);
     }
     cp_async_mbar_arrive_noinc(q_full);
-    // K/V tiles: every lane owns one 16-byte chunk column c and rows r0 + 4i; all row bases are hoisted out of
-    // the tile loop (the loader is a single warp: per-element 64-bit index arithmetic was the bottleneck)
-    const int c = lane & 7, r0 = lane >> 3;
-    const __nv_bfloat16* kcol = (c < 4 ? kh : kl) + (long long)bkv * d.Nk * d.ldk + d.k_col + h * ATT_D + (c & 3) * 8;
-    const long long vrow0 = ((long long)(bkv * d.heads + h) * ATT_D + r0) * d.ld_t + c * 8;
-    const long long kstep = 4ll * d.ldk, vstep = 4ll * d.ld_t;
+    // K/V tiles: all row bases are hoisted out of the tile loop (the loader is a single warp: per-element 64-bit index
+    // arithmetic was the bottleneck).  K: lane -> chunk ck (of 4), rows rk + 8i; V^T: lane -> chunk cv (of 8), rows rv + 4i.
+    const int ck = lane & 3, rk = lane >> 2;
+    const int cv = lane & 7, rv = lane >> 3;
+    const aldm_plane_t* kcol = kh + (long long)bkv * d.Nk * d.ldk + d.k_col + h * ATT_D + ck * 8;
+    const long long vrow0 = ((long long)(bkv * d.heads + h) * ATT_D + rv) * d.ld_t + cv * 8;
+    const long long kstep = 8ll * d.ldk, vstep = 4ll * d.ld_t;
     for (int it = 0, s = 0, ph = 1; it < nt; ++it) {
       const int k0 = it * KT;
       mbar_wait(kv_empty0 + 8 * s, ph);
       const uint32_t kb = base + KB + s * (KT * 128);
-      const __nv_bfloat16* kp = kcol + (long long)(k0 + r0) * d.ldk;
+      const aldm_plane_t* kp = kcol + (long long)(k0 + rk) * d.ldk;
 #pragma unroll
-      for (int i = 0; i < KT / 4; ++i) {
-        const int r = r0 + 4 * i;
+      for (int i = 0; i < KT / 8; ++i) {
+        const int r = rk + 8 * i;
         const bool ok = k0 + r < d.Nk;
-        cp_async_16(kb + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), ok ? kp + i * kstep : kcol, ok ? 16u : 0u);
+        cp_async_16(kb + r * 128 + ((uint32_t)(ck ^ (r & 7)) << 4), ok ? kp + i * kstep : kcol, ok ? 16u : 0u);
       }
-      const uint32_t vb = base + VT + s * (2 * ATT_D * 128);
-      const bool vok = k0 + c * 8 < d.Nk;
+      const uint32_t vb = base + VT + s * (ATT_D * 128);
+      const bool vok = k0 + cv * 8 < d.Nk;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int pl = i >> 3, r = r0 + 4 * (i & 7);
-        const __nv_bfloat16* vp = (pl ? vl : vh) + vrow0 + (i & 7) * vstep + k0;
-        cp_async_16(vb + pl * (ATT_D * 128) + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), vok ? vp : vh, vok ? 16u : 0u);
+      for (int i = 0; i < ATT_D / 4; ++i) {
+        const int r = rv + 4 * i;
+        const aldm_plane_t* vp = vh + vrow0 + i * vstep + k0;
+        cp_async_16(vb + r * 128 + ((uint32_t)(cv ^ (r & 7)) << 4), vok ? vp : vh, vok ? 16u : 0u);
       }
       cp_async_mbar_arrive_noinc(kv_full0 + 8 * s);
       if (++s == NS) { s = 0; ph ^= 1; }
@@ -239,22 +235,18 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
   } else {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      constexpr uint32_t idS = umma_idesc_bf16(128, KT), idO = umma_idesc_bf16(128, ATT_D);
+      constexpr uint32_t idS = umma_idesc_f16(128, KT), idO = umma_idesc_f16(128, ATT_D);
       const uint64_t dQ = umma_desc_sw128(base + QA);
-      const uint64_t dPh = umma_desc_sw128(base + PP), dPl = umma_desc_sw128(base + PP + QT * 128);
+      const uint64_t dP = umma_desc_sw128(base + PP);
       auto issue_S = [&](int t) {      // S(t) = Q K(t)^T into TMEM buffer t & 1
         const int st = t % NS;
         mbar_wait(kv_full0 + 8 * st, (t / NS) & 1);      // returns at once when the caller has already seen it complete
         tc_fence_after();
         const uint64_t dK = umma_desc_sw128(base + KB + st * (KT * 128));
         const uint32_t tS = tmem_S + (t & 1) * KT;
-        // descriptor address units are 16 bytes: +2 = next K-step of 16 bf16, +4 = the lo half of the row
+        // descriptor address units are 16 bytes: +2 = next K-step of 16 fp16
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dQ + 4 + 2 * ks, dK + 2 * ks, idS, ks > 0);     // q_lo k_hi
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dQ + 2 * ks, dK + 4 + 2 * ks, idS, 1);          // q_hi k_lo
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) umma_bf16(tS, dQ + 2 * ks, dK + 2 * ks, idS, 1);              // q_hi k_hi
+        for (int ks = 0; ks < 2; ++ks) umma_f16(tS, dQ + 2 * ks, dK + 2 * ks, idS, ks > 0);
         umma_commit(s_full0 + 8 * (t & 1));
       };
       mbar_wait(q_full, 0);
@@ -268,14 +260,9 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         if (!s_next && mbar_test_wait(kv_full0 + 8 * ((it + 1) % NS), ((it + 1) / NS) & 1)) { issue_S(it + 1); s_next = true; }
         mbar_wait(p_full, it & 1);
         tc_fence_after();
-        const uint64_t dVh = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128));
-        const uint64_t dVl = umma_desc_sw128(base + VT + s * (2 * ATT_D * 128) + ATT_D * 128);
+        const uint64_t dV = umma_desc_sw128(base + VT + s * (ATT_D * 128));
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          umma_bf16(tmem_O, dPl + 2 * ks, dVh + 2 * ks, idO, ks > 0);
-          umma_bf16(tmem_O, dPh + 2 * ks, dVl + 2 * ks, idO, 1);
-          umma_bf16(tmem_O, dPh + 2 * ks, dVh + 2 * ks, idO, 1);
-        }
+        for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_O, dP + 2 * ks, dV + 2 * ks, idO, ks > 0);
         umma_commit(o_full);
         umma_commit(kv_empty0 + 8 * s);
         if (!s_next) issue_S(it + 1);
@@ -293,7 +280,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
 // The tensor-core kernel pays its whole fixed cost (TMEM allocation, three mbarrier hand-overs, a 64-key
 // tile that is mostly padding) for ~0.1 GFLOP: 37 us per launch in the step's launch list, 32 launches
 // per DDIM step.  Here one thread owns one query, K and V of the (batch, head) sit in shared memory as
-// fp32 (hi + lo is exact in fp32), and the 2 x Nk x 32 FMAs per query run on the CUDA cores.
+// fp32 (converted from their fp16 planes), and the 2 x Nk x 32 FMAs per query run on the CUDA cores.
 // ------------------------------------------------------------------------------------------------
 template <int NKT>
 __global__ void __launch_bounds__(128) attention_short_kernel(const __grid_constant__ aldm_attn_desc d) {
@@ -305,18 +292,16 @@ __global__ void __launch_bounds__(128) attention_short_kernel(const __grid_const
   const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
   pdl_wait();
   {
-    const __nv_bfloat16* kh = reinterpret_cast<const __nv_bfloat16*>(d.k_hi);
-    const __nv_bfloat16* kl = reinterpret_cast<const __nv_bfloat16*>(d.k_lo);
-    const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(d.vt_hi);
-    const __nv_bfloat16* vl = reinterpret_cast<const __nv_bfloat16*>(d.vt_lo);
+    const aldm_plane_t* kh = reinterpret_cast<const aldm_plane_t*>(d.k_hi);
+    const aldm_plane_t* vh = reinterpret_cast<const aldm_plane_t*>(d.vt_hi);
     for (int idx = tid; idx < NKT * ATT_D; idx += 128) {
       const int key = idx / ATT_D, dim = idx % ATT_D;
       float kv = 0.f, vv = 0.f;
       if (key < d.Nk) {
         const long long ki = ((long long)bkv * d.Nk + key) * d.ldk + d.k_col + h * ATT_D + dim;
         const long long vi = ((long long)(bkv * d.heads + h) * ATT_D + dim) * d.ld_t + key;
-        kv = __bfloat162float(kh[ki]) + __bfloat162float(kl[ki]);
-        vv = __bfloat162float(vh[vi]) + __bfloat162float(vl[vi]);
+        kv = plane_to_f(kh[ki]);
+        vv = plane_to_f(vh[vi]);
       }
       sk[key][dim] = kv;
       sv[key][dim] = vv;
@@ -330,16 +315,16 @@ __global__ void __launch_bounds__(128) attention_short_kernel(const __grid_const
   float qv[ATT_D];
   {
     const long long qi = ((long long)b * d.Nq + q) * d.ldq + d.q_col + h * ATT_D;
-    const uint4* ph = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.q_hi) + qi);
-    const uint4* pl = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.q_lo) + qi);
+    const uint4* ph = reinterpret_cast<const uint4*>(reinterpret_cast<const aldm_plane_t*>(d.q_hi) + qi);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const uint4 a = __ldg(ph + c), l = __ldg(pl + c);
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, lw[4] = {l.x, l.y, l.z, l.w};
+      const uint4 a = __ldg(ph + c);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {      // bf16 -> fp32 is a 16-bit shift
-        qv[c * 8 + 2 * e] = __uint_as_float(aw[e] << 16) + __uint_as_float(lw[e] << 16);
-        qv[c * 8 + 2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2(aw[e]);
+        qv[c * 8 + 2 * e] = f.x;
+        qv[c * 8 + 2 * e + 1] = f.y;
       }
     }
   }
@@ -382,16 +367,7 @@ __global__ void __launch_bounds__(128) attention_short_kernel(const __grid_const
   const float inv = 1.0f / l;
 #pragma unroll
   for (int i = 0; i < ATT_D; ++i) o[i] *= inv;
-  const long long orow = (long long)b * d.Nq + q;
-  __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + h * ATT_D;
-  __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + h * ATT_D;
-#pragma unroll
-  for (int i = 0; i < ATT_D; i += 8) {
-    uint4 hh, ll;
-    split8(o + i, hh, ll);
-    *reinterpret_cast<uint4*>(hp + i) = hh;
-    *reinterpret_cast<uint4*>(lp + i) = ll;
-  }
+  store_out_row(d, (long long)b * d.Nq + q, h, o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -402,9 +378,8 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const __grid_consta
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= d.Nq) return;
   const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
-  auto ld = [](const void* hi, const void* lo, long long i) {
-    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(hi)[i]) +
-           __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(lo)[i]);
+  auto ld = [](const void* hi, const void* /*lo: the attention operands are single-plane*/, long long i) {
+    return plane_to_f(reinterpret_cast<const aldm_plane_t*>(hi)[i]);
   };
   float q[ATT_D], o[ATT_D];
   for (int i = 0; i < ATT_D; ++i) {
@@ -425,27 +400,19 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const __grid_consta
       o[i] = o[i] * corr + p * ld(d.vt_hi, d.vt_lo, ((long long)(bkv * d.heads + h) * ATT_D + i) * d.ld_t + k);
     mrun = mnew;
   }
-  const long long orow = (long long)b * d.Nq + qi;
-  __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + h * ATT_D;
-  __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + h * ATT_D;
-  for (int i = 0; i < ATT_D; ++i) {
-    const float v = o[i] / lrun;
-    const __nv_bfloat16 hh = __float2bfloat16_rn(v);
-    hp[i] = hh;
-    lp[i] = __float2bfloat16_rn(v - __bfloat162float(hh));
-  }
+  for (int i = 0; i < ATT_D; ++i) o[i] /= lrun;
+  store_out_row(d, (long long)b * d.Nq + qi, h, o);
 }
 
 int attention_launch(const aldm_attn_desc& d, cudaStream_t st) {
-  ALDM_REQUIRE(d.q_hi && d.q_lo && d.k_hi && d.k_lo && d.vt_hi && d.vt_lo && d.out_hi && d.out_lo, ALDM_E_ARG,
-               "attention: null pointer");
+  // single-plane operands: the *_lo inputs are ignored; out_lo is written only when non-NULL
+  ALDM_REQUIRE(d.q_hi && d.k_hi && d.vt_hi && d.out_hi, ALDM_E_ARG, "attention: null pointer");
   ALDM_REQUIRE(d.B > 0 && d.heads > 0 && d.Nq > 0 && d.Nk > 0, ALDM_E_SHAPE, "attention: B=%d heads=%d Nq=%d Nk=%d", d.B,
                d.heads, d.Nq, d.Nk);
   ALDM_REQUIRE(d.ldq % 8 == 0 && d.ldk % 8 == 0 && d.ld_t % 8 == 0 && d.ldo % 8 == 0 && d.q_col % 8 == 0 && d.k_col % 8 == 0,
                ALDM_E_ALIGN, "attention: leading dims / column offsets must be multiples of 8");
   ALDM_REQUIRE(d.ld_t >= d.Nk, ALDM_E_SHAPE, "attention: ld_t=%d < Nk=%d", d.ld_t, d.Nk);
-  ALDM_REQUIRE(aligned16(d.q_hi) && aligned16(d.q_lo) && aligned16(d.k_hi) && aligned16(d.k_lo) && aligned16(d.vt_hi) &&
-                   aligned16(d.vt_lo) && aligned16(d.out_hi) && aligned16(d.out_lo),
+  ALDM_REQUIRE(aligned16(d.q_hi) && aligned16(d.k_hi) && aligned16(d.vt_hi) && aligned16(d.out_hi) && aligned16(d.out_lo),
                ALDM_E_ALIGN, "attention: pointers must be 16B aligned");
   ALDM_REQUIRE(d.heads <= 65535 && d.B <= 65535, ALDM_E_SHAPE, "attention: grid too large");
   if (d.impl == ALDM_GEMM_SIMT) {
@@ -457,26 +424,22 @@ int attention_launch(const aldm_attn_desc& d, cudaStream_t st) {
     else if (d.Nk <= 16) ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<16>, grid, dim3(128), 0, st, d));
     else ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<32>, grid, dim3(128), 0, st, d));
   } else {
-    static int stages = 0;
-    if (stages == 0) {
-      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<2>::SMEM));
-      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<3>::SMEM));
-      // Both layouts are 97 KB (two CTAs per SM).  cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for either
-      // (the 2-stage kernel measurably runs two per SM under ncu), so it is not consulted.  ALDM_ATTN_STAGES=2 = A/B switch.
-      const char* e = getenv("ALDM_ATTN_STAGES");
-      stages = (e && e[0] == '2') ? 2 : 3;
+    static bool configured = false;
+    constexpr int NS = 4;       // 81 KB: two CTAs per SM (TMEM: 2 x 256 columns)
+    if (!configured) {
+      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<NS>::SMEM));
+      configured = true;
     }
     dim3 grid(cdiv(d.Nq, atc::QT), d.heads, d.B);
-    if (stages == 3) ALDM_CHECK_CUDA(launch_pdl(attention_tc_kernel<3>, grid, dim3(192), atc::Cfg<3>::SMEM, st, d));
-    else ALDM_CHECK_CUDA(launch_pdl(attention_tc_kernel<2>, grid, dim3(192), atc::Cfg<2>::SMEM, st, d));
+    ALDM_CHECK_CUDA(launch_pdl(attention_tc_kernel<NS>, grid, dim3(192), atc::Cfg<NS>::SMEM, st, d));
   }
   ALDM_CHECK_CUDA(cudaGetLastError());
   return ALDM_OK;
 }
 
 // row softmax of x[rows, n] (x already scaled when scale == 1) -> planes [rows, n]; one block per row
-__global__ void softmax_rows_kernel(const float* __restrict__ x, int n, float scale, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo) {
+__global__ void softmax_rows_kernel(const float* __restrict__ x, int n, float scale, aldm_plane_t* __restrict__ hi,
+                                    aldm_plane_t* __restrict__ lo) {
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* xp = x + row * n;
@@ -503,10 +466,9 @@ __global__ void softmax_rows_kernel(const float* __restrict__ x, int n, float sc
     split2(a, b, h, l);
     if (i + 1 < n) {
       *reinterpret_cast<uint32_t*>(hi + row * n + i) = h;
-      *reinterpret_cast<uint32_t*>(lo + row * n + i) = l;
+      if (lo) *reinterpret_cast<uint32_t*>(lo + row * n + i) = l;
     } else {
-      hi[row * n + i] = __float2bfloat16_rn(a);
-      lo[row * n + i] = __float2bfloat16_rn(a - __bfloat162float(__float2bfloat16_rn(a)));
+      store_split1(hi, lo, row * n + i, a);
     }
   }
 }
@@ -521,10 +483,10 @@ extern "C" int aldm_attention(const aldm_attn_desc* d, void* stream) {
 extern "C" int aldm_softmax_rows(const float* x, int32_t rows, int32_t n, float scale, void* out_hi, void* out_lo,
                                  void* stream) {
   using namespace aldm;
-  ALDM_REQUIRE(x && out_hi && out_lo && rows > 0 && n > 0, ALDM_E_ARG, "softmax_rows: bad arguments");
+  ALDM_REQUIRE(x && out_hi && rows > 0 && n > 0, ALDM_E_ARG, "softmax_rows: bad arguments");
   ALDM_REQUIRE(n % 2 == 0, ALDM_E_UNSUPPORTED, "softmax_rows: n must be even");
   softmax_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, n, scale, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo));
+      x, n, scale, reinterpret_cast<aldm_plane_t*>(out_hi), reinterpret_cast<aldm_plane_t*>(out_lo));
   ALDM_CHECK_CUDA(cudaGetLastError());
   return ALDM_OK;
 }

@@ -3,7 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -64,19 +64,35 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 // ------------------------------------------------------------------------------------------
-// bf16 hi/lo split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|
+// fp16 operand planes.  hi = fp16(x) carries 11 significand bits; lo = fp16(x - hi) adds 11 more (|x - hi - lo| <=
+// 2^-22 |x| while lo stays normal, <= 2^-25 absolute once it is subnormal).  Two-plane operands feed three tensor-core
+// passes (hi*hi + hi*lo + lo*hi), single-plane activations two (hi*w_hi + hi*w_lo).  Inputs saturate at the fp16 range
+// (+-65504) so that x - hi can never be inf - inf; activations behind a normalisation / gating stay far inside it.
 // ------------------------------------------------------------------------------------------
+typedef __half aldm_plane_t;
+__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  float ra = a - __bfloat162float(h.x);
-  float rb = b - __bfloat162float(h.y);
-  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  a = sat_f16(a);
+  b = sat_f16(b);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-
-__device__ __forceinline__ float bf16lo_to_f(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16hi_to_f(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2_hi(float a, float b) {       // hi plane only
+  const __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ float plane_to_f(aldm_plane_t v) { return __half2float(v); }
+// scalar element store: hi (and lo when the operand has a second plane)
+__device__ __forceinline__ void store_split1(aldm_plane_t* hp, aldm_plane_t* lp, long long i, float v) {
+  v = sat_f16(v);
+  const __half h = __float2half_rn(v);
+  hp[i] = h;
+  if (lp) lp[i] = __float2half_rn(v - __half2float(h));
+}
 
 // 8 consecutive floats -> one 16-byte chunk of hi and one of lo
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
@@ -84,6 +100,9 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   split2(v[2], v[3], hi.y, lo.y);
   split2(v[4], v[5], hi.z, lo.z);
   split2(v[6], v[7], hi.w, lo.w);
+}
+__device__ __forceinline__ uint4 pack8_hi(const float* v) {
+  return make_uint4(pack2_hi(v[0], v[1]), pack2_hi(v[2], v[3]), pack2_hi(v[4], v[5]), pack2_hi(v[6], v[7]));
 }
 
 // x * sigmoid(x) with approximate reciprocal (the IEEE division expands to ~20 instructions with a guarded slow path;
@@ -227,8 +246,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands, fp32 accumulate, cta_group::1
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem]^T, 16-bit float operands (format in the instruction descriptor), fp32 accumulate, cta_group::1
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -263,10 +282,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// Instruction descriptor (InstrDescriptor): c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13),
+// Instruction descriptor (InstrDescriptor): c_format F32=1 [4,6), a/b_format F16=0 [7,10)/[10,13) (BF16 would be 1),
 // a/b major K=0, n_dim = N>>3 [17,23), m_dim = M>>4 [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace aldm

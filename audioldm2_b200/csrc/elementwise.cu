@@ -47,7 +47,7 @@ __global__ void masked_blend_kernel(float* __restrict__ img, const float* __rest
 }
 
 __global__ void temb_kernel(const long long* __restrict__ t, int B, int dim, const float* __restrict__ freqs,
-                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                            aldm_plane_t* __restrict__ hi, aldm_plane_t* __restrict__ lo) {
   pdl_wait();
   const int half = dim >> 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,11 +58,8 @@ __global__ void temb_kernel(const long long* __restrict__ t, int B, int dim, con
   // args = t.float() * freqs (util.py:188) is an exact fp32 product.
   const float arg = (float)t[b] * __ldg(freqs + i);
   const float cv = cosf(arg), sv = sinf(arg);
-  const __nv_bfloat16 ch = __float2bfloat16_rn(cv), sh = __float2bfloat16_rn(sv);
-  hi[(long long)b * dim + i] = ch;
-  lo[(long long)b * dim + i] = __float2bfloat16_rn(cv - __bfloat162float(ch));
-  hi[(long long)b * dim + half + i] = sh;
-  lo[(long long)b * dim + half + i] = __float2bfloat16_rn(sv - __bfloat162float(sh));
+  store_split1(hi, lo, (long long)b * dim + i, cv);
+  store_split1(hi, lo, (long long)b * dim + half + i, sv);
 }
 
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int to_nhwc,
@@ -142,12 +139,12 @@ extern "C" int aldm_masked_blend(float* img, const float* x0, const float* mask,
 
 extern "C" int aldm_timestep_embedding(const int64_t* t, int32_t B, int32_t dim, const float* freqs, void* out_hi,
                                        void* out_lo, void* stream) {
-  ALDM_REQUIRE(t && freqs && out_hi && out_lo, ALDM_E_ARG, "timestep_embedding: null pointer");
+  ALDM_REQUIRE(t && freqs && out_hi, ALDM_E_ARG, "timestep_embedding: null pointer");      // out_lo == NULL: hi plane only
   ALDM_REQUIRE(B > 0 && dim > 0 && dim % 8 == 0, ALDM_E_SHAPE, "timestep_embedding: B=%d dim=%d", B, dim);
   const int n = B * (dim / 2);
   temb_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(t), B, dim, freqs, reinterpret_cast<__nv_bfloat16*>(out_hi),
-      reinterpret_cast<__nv_bfloat16*>(out_lo));
+      reinterpret_cast<const long long*>(t), B, dim, freqs, reinterpret_cast<aldm_plane_t*>(out_hi),
+      reinterpret_cast<aldm_plane_t*>(out_lo));
   ALDM_CHECK_CUDA(cudaGetLastError());
   return ALDM_OK;
 }

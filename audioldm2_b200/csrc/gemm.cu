@@ -2,11 +2,13 @@
 //
 //   out[row(m), n] = epilogue( sum_k A[m,k] * W[n,k] )        (aldm_gemm_desc, include/aldm_b200.h)
 //
-// Precision: fp32-faithful "bf16x3".  Activations arrive as two bf16 planes (x ~= hi + lo,
-// written by the prep kernels / producer epilogues) and weights are packed hi/lo the same way;
-// each K step issues three kind::f16 UMMAs (hi*hi, hi*lo, lo*hi) into one fp32 TMEM
-// accumulator, which restores ~2^-17 relative operand precision at 1/3 of the bf16 tensor rate
-// (plain bf16 misses the 1e-3 waveform tolerance by an order of magnitude).
+// Precision: split-fp16 operands, fp32 accumulation in TMEM.  Weights are packed as two fp16 planes (w ~= hi + lo,
+// 22 significand bits).  Activations arrive as fp16 planes written by the prep kernels / producer epilogues:
+//   * two planes (a_lo != NULL): three kind::f16 UMMAs per K step (lo*hi, hi*lo, hi*hi), ~2^-22 operand precision --
+//     the convolutions, where the 200-step waveform budget goes (scripts/precision_study.py);
+//   * one plane (a_lo == NULL): two UMMAs (hi*lo_w, hi*hi_w) and half the A bytes -- the token-side linear layers.
+// (plain single-pass bf16 / TF32-class rounding of BOTH operands misses or crowds the 1e-3 waveform
+// tolerance; rounding only the activations to 11 bits costs 2e-4 at 200 steps.)
 //
 // Structure of one CTA (192 threads, one 128 x BN output tile, optional split-K slice):
 //   warps 0-3  A producers: gather 16-byte chunks (8 channels of one tap of one pixel) with
@@ -16,9 +18,6 @@
 //   warp 4     B producer: one elected lane issues a TMA bulk copy (cp.async.bulk) of the
 //              host-packed, pre-swizzled weight tile image (hi|lo) per stage.
 //   warp 5     allocates TMEM; one elected lane issues tcgen05.mma and commits stages.
-#ifdef ALDM_EXPERIMENTAL_TMA
-#include <cuda.h>
-#endif
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -70,51 +69,36 @@ __device__ __forceinline__ void epi_finish(const aldm_gemm_desc& d, const RowInf
       for (int i = 0; i < cnt; ++i) op[i] = v[i];
     }
     if (d.out_hi) {   // dual output: the same values also as operand planes for the next GEMM
-      __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + r.orow * d.ldo + n0;
-      __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + r.orow * d.ldo + n0;
-      for (int i = 0; i < cnt; ++i) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
-        hp[i] = h;
-        lp[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
-      }
+      aldm_plane_t* hp = reinterpret_cast<aldm_plane_t*>(d.out_hi) + r.orow * d.ldo + n0;
+      aldm_plane_t* lp = d.out_lo ? reinterpret_cast<aldm_plane_t*>(d.out_lo) + r.orow * d.ldo + n0 : nullptr;
+      for (int i = 0; i < cnt; ++i) store_split1(hp, lp, i, v[i]);
     }
   } else if (d.out_mode == ALDM_OUT_QKV && n0 >= d.n_split) {
     // V projection: transposed planes [(b*Cv + c), ld_t] with the token index contiguous
     const int b = r.m / d.tok_per_batch, tok = r.m - b * d.tok_per_batch;
     const long long base = ((long long)b * (d.N - d.n_split) + (n0 - d.n_split)) * d.ld_t + tok;
-    __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out2_hi) + base;
-    __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out2_lo) + base;
-    for (int i = 0; i < cnt; ++i) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
-      hp[(long long)i * d.ld_t] = h;
-      lp[(long long)i * d.ld_t] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
-    }
+    aldm_plane_t* hp = reinterpret_cast<aldm_plane_t*>(d.out2_hi) + base;
+    aldm_plane_t* lp = d.out2_lo ? reinterpret_cast<aldm_plane_t*>(d.out2_lo) + base : nullptr;
+    for (int i = 0; i < cnt; ++i) store_split1(hp, lp, (long long)i * d.ld_t, v[i]);
     // keys in [tok_per_batch, ld_t) are padding the attention kernel multiplies by P = 0: they must
-    // be finite (stale workspace bytes reinterpreted as bf16 could be NaN), so the last token zeroes them
+    // be finite (stale workspace bytes reinterpreted as fp16 could be NaN), so the last token zeroes them
     if (tok == d.tok_per_batch - 1) {
       for (int t = 1; tok + t < d.ld_t; ++t)
-        for (int i = 0; i < cnt; ++i) {
-          hp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
-          lp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
-        }
+        for (int i = 0; i < cnt; ++i) store_split1(hp, lp, (long long)i * d.ld_t + t, 0.f);
     }
   } else if (d.out_mode == ALDM_OUT_PLANES || d.out_mode == ALDM_OUT_QKV) {
-    __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out_hi) + r.orow * d.ldo + n0;
-    __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out_lo) + r.orow * d.ldo + n0;
+    aldm_plane_t* hp = reinterpret_cast<aldm_plane_t*>(d.out_hi) + r.orow * d.ldo + n0;
+    aldm_plane_t* lp = d.out_lo ? reinterpret_cast<aldm_plane_t*>(d.out_lo) + r.orow * d.ldo + n0 : nullptr;
     if (cnt == 32 && ((reinterpret_cast<uintptr_t>(hp) & 15u) == 0)) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 h, l;
         split8(v + i, h, l);
         *reinterpret_cast<uint4*>(hp + i) = h;
-        *reinterpret_cast<uint4*>(lp + i) = l;
+        if (lp) *reinterpret_cast<uint4*>(lp + i) = l;
       }
     } else {
-      for (int i = 0; i < cnt; ++i) {
-        __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
-        hp[i] = h;
-        lp[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
-      }
+      for (int i = 0; i < cnt; ++i) store_split1(hp, lp, i, v[i]);
     }
   } else {  // NCHW
     for (int i = 0; i < cnt; ++i)
@@ -225,8 +209,8 @@ __device__ __forceinline__ void epi_finish_coalesced(const aldm_gemm_desc& d, co
       uint2 h, l;
       split2(x[0], x[1], h.x, l.x);
       split2(x[2], x[3], h.y, l.y);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + orow * d.ldo + n) = h;
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + orow * d.ldo + n) = l;
+      *reinterpret_cast<uint2*>(reinterpret_cast<aldm_plane_t*>(d.out_hi) + orow * d.ldo + n) = h;
+      if (d.out_lo) *reinterpret_cast<uint2*>(reinterpret_cast<aldm_plane_t*>(d.out_lo) + orow * d.ldo + n) = l;
     }
   }
   __syncwarp();
@@ -289,8 +273,8 @@ __device__ __forceinline__ void emit_rows(const aldm_gemm_desc& d, const CR& cr,
       uint2 h, l;
       split2(x.x, x.y, h.x, l.x);
       split2(x.z, x.w, h.y, l.y);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + o) = h;
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + o) = l;
+      *reinterpret_cast<uint2*>(reinterpret_cast<aldm_plane_t*>(d.out_hi) + o) = h;
+      if (d.out_lo) *reinterpret_cast<uint2*>(reinterpret_cast<aldm_plane_t*>(d.out_lo) + o) = l;
     }
   }
   __syncwarp();
@@ -299,198 +283,22 @@ __device__ __forceinline__ void emit_rows(const aldm_gemm_desc& d, const CR& cr,
 // ------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------
-template <int BN>
-struct TcCfg {
+template <int BN, int AP>
+struct Tc3Cfg {
   static constexpr int BM = 128;
-  static constexpr int BK = 64;                       // bf16 elements = 128 bytes per row
+  static constexpr int BK = 64;                       // fp16 elements = 128 bytes per row
   static constexpr int A_BYTES = BM * 128;            // one plane
   static constexpr int B_BYTES = BN * 128;            // one plane
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int STG_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose staging (persistent kernel)
-  static constexpr int SMEM2_BYTES = SMEM_BYTES + STG_BYTES;
+  static constexpr int STAGE_BYTES = AP * A_BYTES + 2 * B_BYTES;      // [a_hi | a_lo (AP == 2)] [b_hi | b_lo]
+  static constexpr int B_OFF = AP * A_BYTES;
+  static constexpr int STG_BYTES = 8 * 32 * 33 * 4;   // one 32x33 fp32 transpose tile per epilogue warp
+  static constexpr int SMEM_MAX = 227 * 1024;
+  static constexpr int FIT = (SMEM_MAX - 1024 - 256 - STG_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > 4 ? 4 : FIT;    // BN=128: 3 (AP=2, 64 KB stages) / 4 (AP=1, 48 KB)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
   static constexpr int TMEM_COLS = BN;                // power of two >= 32
+  static_assert(STAGES >= 2, "pipeline needs two stages");
 };
-
-template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ aldm_gemm_desc d) {
-  using C = TcCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  const int M = d.B * d.OH * d.OW;
-  const int m0 = blockIdx.x * C::BM;
-  const int ntile = blockIdx.y;
-  const int nkb_total = d.Kpad / C::BK;
-  const int kb_begin = (int)(((long long)blockIdx.z * nkb_total) / d.splitk);
-  const int kb_end = (int)(((long long)(blockIdx.z + 1) * nkb_total) / d.splitk);
-  const int nkb = kb_end - kb_begin;
-
-  if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 128 + 1);   // 128 cp.async producers + 1 expect_tx arrive
-      mbar_init(empty_bar(s), 1);        // tcgen05.commit
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp < 4) {
-    // ===================== A producers =====================
-    const int j = tid & 7;                 // 16-byte chunk (8 channels) inside the 64-wide K block
-    const int rbase = tid >> 3;            // rows rbase + 16*i
-    const uint32_t swz = (uint32_t)((j ^ (rbase & 7)) << 4);
-    int ih0[8], iw0[8], pb[8];             // pb < 0 => row out of range
-    const int Hs = d.H >> d.up, Ws = d.W >> d.up;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m = m0 + rbase + 16 * i;
-      if (m < M) {
-        int ow = m % d.OW;
-        int t = m / d.OW;
-        int oh = t % d.OH;
-        int b = t / d.OH;
-        ih0[i] = oh * d.sy;
-        iw0[i] = ow * d.sx;
-        pb[i] = (d.bmod > 0 ? b % d.bmod : b) * Hs;
-      } else {
-        ih0[i] = 0; iw0[i] = 0; pb[i] = -1;
-      }
-    }
-    const __nv_bfloat16* ahi = reinterpret_cast<const __nv_bfloat16*>(d.a_hi);
-    const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(d.a_lo);
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % C::STAGES;
-      mbar_wait(empty_bar(s), ((it / C::STAGES) & 1) ^ 1);
-      const int k = (kb_begin + it) * C::BK + j * 8;
-      const bool kvalid = k < d.K;
-      int tap = 0, c = 0;
-      if (kvalid) { tap = k / d.Cp; c = k - tap * d.Cp; }
-      const int dy = d.dy[tap], dx = d.dx[tap];
-      const uint32_t sa = base + s * C::STAGE_BYTES + swz;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int ih = ih0[i] + dy, iw = iw0[i] + dx;
-        const bool ok = kvalid && pb[i] >= 0 && ih >= 0 && ih < d.H && iw >= 0 && iw < d.W;
-        long long off = 0;
-        if (ok) off = ((long long)(pb[i] + (ih >> d.up)) * Ws + (iw >> d.up)) * d.Cp + c;
-        const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
-        cp_async_16(dst, ahi + off, ok ? 16u : 0u);
-        cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
-      }
-      cp_async_mbar_arrive_noinc(full_bar(s));
-    }
-
-    // ===================== epilogue =====================
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int m = m0 + tid;
-    const RowInfo r = decode_row(d, m, M);
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    if (d.splitk > 1) {
-      const int Mpad = gridDim.x * C::BM, Npad = gridDim.y * BN;
-      float* wp = d.ws + ((long long)blockIdx.z * Mpad + m) * Npad + ntile * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(trow + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(wp + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      }
-    } else if (d.act == ALDM_ACT_GEGLU) {
-      const int n_out = d.N / 2;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-        uint32_t vr[32], gr[32];
-        tmem_ld32(trow + c0, vr);
-        tmem_ld32(trow + BN / 2 + c0, gr);
-        tmem_ld_wait();
-        float* v = reinterpret_cast<float*>(vr);
-        float* g = reinterpret_cast<float*>(gr);
-        epi_activate(d, r, ntile * BN + c0, v, g);
-        epi_finish(d, r, ntile * (BN / 2) + c0, 32, v, n_out);
-      }
-    } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t vr[32];
-        tmem_ld32(trow + c0, vr);
-        tmem_ld_wait();
-        float* v = reinterpret_cast<float*>(vr);
-        epi_activate(d, r, ntile * BN + c0, v, nullptr);
-        epi_finish(d, r, ntile * BN + c0, 32, v, d.N);
-      }
-    }
-    tc_fence_before();
-  } else if (warp == 4) {
-    // ===================== B producer (TMA bulk copy of packed tile images) =====================
-    if (lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(d.w_packed) +
-                            ((long long)ntile * nkb_total + kb_begin) * (2 * C::B_BYTES);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % C::STAGES;
-        mbar_wait(empty_bar(s), ((it / C::STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
-        bulk_g2s(base + s * C::STAGE_BYTES + 2 * C::A_BYTES, wsrc + (long long)it * (2 * C::B_BYTES),
-                 2 * C::B_BYTES, full_bar(s));
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % C::STAGES;
-        mbar_wait(full_bar(s), (it / C::STAGES) & 1);
-        tc_fence_after();
-        fence_proxy_async();
-        const uint32_t sa = base + s * C::STAGE_BYTES;
-        const uint64_t da_hi = umma_desc_sw128(sa);
-        const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);
-        const uint64_t db_hi = umma_desc_sw128(sa + 2 * C::A_BYTES);
-        const uint64_t db_lo = umma_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {            // 4 x K=16 (32 bytes) inside the 128B swizzle row
-          const uint64_t o = (uint64_t)(ks * 2);    // +32 bytes in the (addr >> 4) field
-          umma_bf16(tmem_base, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
-          umma_bf16(tmem_base, da_hi + o, db_lo + o, idesc, 1);
-          umma_bf16(tmem_base, da_hi + o, db_hi + o, idesc, 1);
-        }
-        umma_commit(empty_bar(s));
-      }
-      umma_commit(tmem_full_bar);
-    }
-    __syncwarp();
-  }
-
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
 
 // Debug timeline (profiling aid, dbg bit 128): CTA 0 records clock64() at pipeline events.
 // layout: [role 0..3][iteration 0..255][phase 0..1]
@@ -547,35 +355,11 @@ struct Tc3Divs {
   int plain;      // 1x1 tap, unit stride, no upsample / batch-modulo: input row == output row (linear layers)
 };
 
-template <int BN>
-struct Tc3Cfg : TcCfg<BN> {
-  // BN = 256 (planner switch ALDM_BN256, EXPERIMENTAL / not yet validated on hardware): 96 KB stages, two of them --
-  // the same bytes in flight as 3 x 64 KB, with 25% fewer operand bytes per FLOP and half the A-gather work.
-  static constexpr int STAGES = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);
-  static constexpr int STG_BYTES = 8 * 32 * 33 * 4;     // one 32x33 fp32 transpose tile per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * TcCfg<BN>::STAGE_BYTES + 1024 + 256 + STG_BYTES;
-};
-
-// TMA = true (EXPERIMENTAL, ALDM_TMA_A=1, not yet validated on hardware): linear layers fetch the A tile with two
-// cp.async.bulk.tensor loads per stage (hi and lo plane; 2-D tensor maps over [rows, Cp] bf16 with 128-byte swizzle and
-// zero fill past the last row / channel) issued by ONE thread, instead of 128 threads x 16 cp.async each.  The maps ride
-// in a trailing kernel parameter that the TMA = false instantiations ignore (their code is unchanged by it).
-// Compiled in only with -DALDM_EXPERIMENTAL_TMA (ALDM_BUILD_EXPERIMENTAL=1 at build time): the default library keeps the
-// validated kernel signature and launch code byte for byte.
-#ifdef ALDM_EXPERIMENTAL_TMA
-struct TmaMaps { CUtensorMap hi, lo; };
-
-template <int BN, int EPI, bool TMA = false>
-__global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n,
-                                                           const __grid_constant__ Tc3Divs fd,
-                                                           const __grid_constant__ TmaMaps tm) {
-#else
-template <int BN, int EPI>
+// AP = number of A planes (2: hi + lo, three UMMAs per K step; 1: hi only, two UMMAs and half the A bytes).
+template <int BN, int EPI, int AP>
 __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n,
                                                            const __grid_constant__ Tc3Divs fd) {
-  constexpr bool TMA = false;
-#endif
-  using C = Tc3Cfg<BN>;
+  using C = Tc3Cfg<BN, AP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -597,7 +381,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), TMA ? 2 : 128 + 1);   // 128 cp.async producers (completion-triggered arrivals) + B expect_tx; TMA: A issuer + B
+      mbar_init(full_bar(s), 128 + 1);   // 128 cp.async producers (completion-triggered arrivals) + B expect_tx
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -631,36 +415,14 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     fd.tn.divmod(r, mt, nt);
   };
 
-#ifdef ALDM_EXPERIMENTAL_TMA
-  if (TMA && warp < 4) {
-    // ===================== A by TMA: one thread, two tensor loads per stage =====================
-    if (tid == 0) {
-      pdl_wait();
-      uint32_t cnt = 0;
-      for (int id = blockIdx.x; id < total; id += gridDim.x) {
-        int mt, nt, z, kb0, nkb;
-        tile_coords(id, mt, nt, z, kb0, nkb);
-        for (int it = 0; it < nkb; ++it, ++cnt) {
-          const int s = cnt % C::STAGES;
-          mbar_wait(empty_bar(s), ((cnt / C::STAGES) & 1) ^ 1);
-          const uint32_t sa = base + s * C::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(s), 2 * C::A_BYTES);
-          tma_load_2d(sa, &tm.hi, (kb0 + it) * C::BK, mt * C::BM, full_bar(s));
-          tma_load_2d(sa + C::A_BYTES, &tm.lo, (kb0 + it) * C::BK, mt * C::BM, full_bar(s));
-        }
-      }
-    }
-    __syncwarp();
-  } else
-#endif
   if (warp < 4) {
     // ===================== A producers =====================
     const int j = tid & 7;                 // 16-byte chunk (8 channels) inside the 64-wide K block
     const int rbase = tid >> 3;            // rows rbase + 16*i
     const uint32_t swz = (uint32_t)((j ^ (rbase & 7)) << 4);
     const int Hs = d.H >> d.up, Ws = d.W >> d.up;
-    const __nv_bfloat16* ahi = reinterpret_cast<const __nv_bfloat16*>(d.a_hi);
-    const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(d.a_lo);
+    const aldm_plane_t* ahi = reinterpret_cast<const aldm_plane_t*>(d.a_hi);
+    const aldm_plane_t* alo = reinterpret_cast<const aldm_plane_t*>(d.a_lo);
     uint32_t cnt = 0;
     int last_mt = -1;
     int rowoff[8];            // element offset of tap (0,0) / channel 0 of each row (valid rows only)
@@ -732,7 +494,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
             const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
             if (!(dbg & 1)) {
               cp_async_16(dst, ahi + off, ok ? 16u : 0u);
-              cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+              if (AP == 2) cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
             }
           }
         } else {      // nearest x2 upsample folded into the gather: source pixel = (ih >> 1, iw >> 1)
@@ -744,7 +506,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
             if (ok) off = ((long long)(pbh[i] + ((ih0[i] + dy) >> 1)) * Ws + ((iw0[i] + dx) >> 1)) * d.Cp + c;
             const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
             cp_async_16(dst, ahi + off, ok ? 16u : 0u);
-            cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+            if (AP == 2) cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
           }
         }
         cp_async_mbar_arrive_noinc(full_bar(s));
@@ -767,7 +529,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           ALDM_TL(1, cnt, 0);
           if (dbg & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_arrive_expect_tx(full_bar(s), 2 * C::B_BYTES);
-          bulk_g2s(base + s * C::STAGE_BYTES + 2 * C::A_BYTES, wsrc + (long long)it * (2 * C::B_BYTES), 2 * C::B_BYTES,
+          bulk_g2s(base + s * C::STAGE_BYTES + C::B_OFF, wsrc + (long long)it * (2 * C::B_BYTES), 2 * C::B_BYTES,
                    full_bar(s));
         }
       }
@@ -776,7 +538,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
       uint32_t cnt = 0, tl = 0;
       for (int id = blockIdx.x; id < total; id += gridDim.x, ++tl) {
         int mt, nt, z, kb0, nkb;
@@ -792,16 +554,16 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           tc_fence_after();
           const uint32_t sa = base + s * C::STAGE_BYTES;
           const uint64_t da_hi = umma_desc_sw128(sa);
-          const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);
-          const uint64_t db_hi = umma_desc_sw128(sa + 2 * C::A_BYTES);
-          const uint64_t db_lo = umma_desc_sw128(sa + 2 * C::A_BYTES + C::B_BYTES);
+          const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);      // only used when AP == 2
+          const uint64_t db_hi = umma_desc_sw128(sa + C::B_OFF);
+          const uint64_t db_lo = umma_desc_sw128(sa + C::B_OFF + C::B_BYTES);
           if (!(dbg & 4)) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {            // 4 x K=16 (32 bytes) inside the 128B swizzle row
               const uint64_t o = (uint64_t)(ks * 2);
-              umma_bf16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
-              umma_bf16(tacc, da_hi + o, db_lo + o, idesc, 1);
-              umma_bf16(tacc, da_hi + o, db_hi + o, idesc, 1);
+              if (AP == 2) umma_f16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
+              umma_f16(tacc, da_hi + o, db_lo + o, idesc, AP == 2 ? 1u : (uint32_t)((it | ks) != 0));     // small terms first
+              umma_f16(tacc, da_hi + o, db_hi + o, idesc, 1);
             }
           }
           umma_commit(empty_bar(s));
@@ -939,23 +701,16 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
             // V projection: transposed planes, lane == token -> consecutive lanes write consecutive bf16
             const int b = r.m / d.tok_per_batch, tok = r.m - b * d.tok_per_batch;
             const long long tb = ((long long)b * (d.N - d.n_split) + (n0 - d.n_split)) * d.ld_t + tok;
-            __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(d.out2_hi) + tb;
-            __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(d.out2_lo) + tb;
+            aldm_plane_t* hp = reinterpret_cast<aldm_plane_t*>(d.out2_hi) + tb;
+            aldm_plane_t* lp = d.out2_lo ? reinterpret_cast<aldm_plane_t*>(d.out2_lo) + tb : nullptr;
             const bool last = tok == d.tok_per_batch - 1;
 #pragma unroll      // full unroll keeps v[] in registers
             for (int i = 0; i < 32; ++i) {
-              if (n0 + i < d.N) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
-                hp[(long long)i * d.ld_t] = h;
-                lp[(long long)i * d.ld_t] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
-              }
+              if (n0 + i < d.N) store_split1(hp, lp, (long long)i * d.ld_t, v[i]);
             }
             if (last) {       // zero the padding keys [tok_per_batch, ld_t) (the attention kernel multiplies them by P = 0)
               for (int i = 0; i < 32 && n0 + i < d.N; ++i)
-                for (int t = 1; tok + t < d.ld_t; ++t) {
-                  hp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
-                  lp[(long long)i * d.ld_t + t] = __float2bfloat16_rn(0.f);
-                }
+                for (int t = 1; tok + t < d.ld_t; ++t) store_split1(hp, lp, (long long)i * d.ld_t + t, 0.f);
             }
           }
         }
@@ -1072,8 +827,8 @@ __global__ void __launch_bounds__(256) splitk_reduce4_kernel(const __grid_consta
     uint2 h, l;
     split2(x.x, x.y, h.x, l.x);
     split2(x.z, x.w, h.y, l.y);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + o) = h;
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + o) = l;
+    *reinterpret_cast<uint2*>(reinterpret_cast<aldm_plane_t*>(d.out_hi) + o) = h;
+    if (d.out_lo) *reinterpret_cast<uint2*>(reinterpret_cast<aldm_plane_t*>(d.out_lo) + o) = l;
   }
 }
 
@@ -1089,8 +844,8 @@ __global__ void gemm_simt_kernel(const __grid_constant__ aldm_gemm_desc d, int N
   const RowInfo r = decode_row(d, m, M);
   const int Hs = d.H >> d.up, Ws = d.W >> d.up;
   const int bsrc = d.bmod > 0 ? r.b % d.bmod : r.b;
-  const __nv_bfloat16* ahi = reinterpret_cast<const __nv_bfloat16*>(d.a_hi);
-  const __nv_bfloat16* alo = reinterpret_cast<const __nv_bfloat16*>(d.a_lo);
+  const aldm_plane_t* ahi = reinterpret_cast<const aldm_plane_t*>(d.a_hi);
+  const aldm_plane_t* alo = reinterpret_cast<const aldm_plane_t*>(d.a_lo);      // NULL: single-plane operand
   const bool geglu = d.act == ALDM_ACT_GEGLU;
   const int nchunks = geglu ? (Npad / d.bn) * (d.bn / 64) : Npad / 32;
   for (int ch = blockIdx.y; ch < nchunks; ch += gridDim.y) {
@@ -1112,7 +867,7 @@ __global__ void gemm_simt_kernel(const __grid_constant__ aldm_gemm_desc d, int N
       const float* wt = wv + tap * d.Cp;
       const float* wgt = wg + tap * d.Cp;
       for (int c = 0; c < d.Cp; ++c) {
-        const float a = __bfloat162float(ahi[off + c]) + __bfloat162float(alo[off + c]);
+        const float a = plane_to_f(ahi[off + c]) + (alo ? plane_to_f(alo[off + c]) : 0.f);
         acc = fmaf(a, __ldg(wt + c), acc);
         if (geglu) accg = fmaf(a, __ldg(wgt + c), accg);
       }
@@ -1134,67 +889,14 @@ __global__ void gemm_simt_kernel(const __grid_constant__ aldm_gemm_desc d, int N
 // ------------------------------------------------------------------------------------------
 // host launch
 // ------------------------------------------------------------------------------------------
-template <int BN>
-static int launch_tc(const aldm_gemm_desc& d, int M, cudaStream_t st) {
-  using C = TcCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
-  }
-  dim3 grid(cdiv(M, C::BM), cdiv(d.N, BN), d.splitk);
-  gemm_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, st>>>(d);
-  ALDM_CHECK_CUDA(cudaGetLastError());
-  if (d.splitk > 1) {
-    const int Mpad = grid.x * C::BM, Npad = grid.y * BN;
-    const int chunks = (d.act == ALDM_ACT_GEGLU) ? (Npad / BN) * (BN / 64) : Npad / 32;
-    const long long total = (long long)M * chunks;
-    splitk_epilogue_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d, Mpad, Npad);
-    ALDM_CHECK_CUDA(cudaGetLastError());
-  }
-  return ALDM_OK;
-}
-
 static int g_num_sms = 0;
 
-#ifdef ALDM_EXPERIMENTAL_TMA
-// ---- tensor maps for the experimental TMA A path (driver entry point fetched at run time: no libcuda link dependency) ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-static bool tma_a_enabled() {
-  static const bool on = [] { const char* e = getenv("ALDM_TMA_A"); return e && e[0] == '1' && encode_tiled_fn() != nullptr; }();
-  return on;
-}
-// [rows, Cp] bf16 plane, box = 64 channels x 128 rows, 128-byte swizzle (the layout the UMMA descriptors expect), zero OOB fill
-static bool make_plane_map(CUtensorMap* tm, const void* base, int rows, int Cp) {
-  const cuuint64_t gdim[2] = {(cuuint64_t)Cp, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)Cp * 2};
-  const cuuint32_t box[2] = {64, 128};
-  const cuuint32_t es[2] = {1, 1};
-  return encode_tiled_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-#endif
-
-template <int BN, int EPI>
-static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
-  using C = Tc3Cfg<BN>;
+template <int BN, int EPI, int AP>
+static int launch_tc3_ap(const aldm_gemm_desc& d, int M, cudaStream_t st) {
+  using C = Tc3Cfg<BN, AP>;
   static bool configured = false;
   if (!configured) {
-    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, EPI, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   if (g_num_sms == 0) {
@@ -1210,29 +912,7 @@ static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   fd.bmod = make_fastdiv(d.bmod > 0 ? d.bmod : 1);
   fd.plain = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.sy == 1 && d.sx == 1 && d.up == 0 && d.bmod <= 0 &&
              d.OH == d.H && d.OW == d.W;
-#ifdef ALDM_EXPERIMENTAL_TMA
-  static TmaMaps no_maps = {};
-  bool launched = false;
-  if constexpr ((EPI == EPI_GEGLU || EPI == EPI_F32N || EPI == EPI_PLN) && BN >= 128) {
-    // EXPERIMENTAL (ALDM_TMA_A=1): linear layers with at least one full K block per row take the tensor-map A path
-    if (tma_a_enabled() && fd.plain && d.Cp >= 64 && aligned16(d.a_hi) && aligned16(d.a_lo)) {
-      static bool configured_tma = false;
-      if (!configured_tma) {
-        ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured_tma = true;
-      }
-      TmaMaps maps;
-      ALDM_REQUIRE(make_plane_map(&maps.hi, d.a_hi, M, d.Cp) && make_plane_map(&maps.lo, d.a_lo, M, d.Cp), ALDM_E_CUDA,
-                   "gemm: cuTensorMapEncodeTiled failed (rows=%d Cp=%d)", M, d.Cp);
-      ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI, true>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd, maps));
-      launched = true;
-    }
-  }
-  if (!launched)
-    ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI, false>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd, no_maps));
-#else
-  ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd));
-#endif
+  ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI, AP>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd));
   ALDM_CHECK_CUDA(cudaGetLastError());
   if (d.splitk > 1) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
@@ -1252,6 +932,11 @@ static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
     ALDM_CHECK_CUDA(cudaGetLastError());
   }
   return ALDM_OK;
+}
+
+template <int BN, int EPI>
+static int launch_tc3_epi(const aldm_gemm_desc& d, int M, cudaStream_t st) {
+  return d.a_lo ? launch_tc3_ap<BN, EPI, 2>(d, M, st) : launch_tc3_ap<BN, EPI, 1>(d, M, st);
 }
 
 template <int BN>
@@ -1281,14 +966,13 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
   const long long Mll = (long long)d.B * d.OH * d.OW;
   ALDM_REQUIRE(Mll > 0 && Mll < (1ll << 31), ALDM_E_SHAPE, "gemm: bad M=%lld", Mll);
   const int M = (int)Mll;
-  ALDM_REQUIRE(d.bn == 32 || d.bn == 64 || d.bn == 128 || (d.bn == 256 && (d.impl & 0xff) != ALDM_GEMM_TC_V1), ALDM_E_UNSUPPORTED,
-               "gemm: bn=%d unsupported", d.bn);
+  ALDM_REQUIRE(d.bn == 32 || d.bn == 64 || d.bn == 128, ALDM_E_UNSUPPORTED, "gemm: bn=%d unsupported", d.bn);
   ALDM_REQUIRE(d.Cp % 8 == 0 && d.Cp > 0, ALDM_E_SHAPE, "gemm: Cp=%d must be a positive multiple of 8", d.Cp);
   ALDM_REQUIRE(d.ntaps >= 1 && d.ntaps <= ALDM_MAX_TAPS, ALDM_E_SHAPE, "gemm: ntaps=%d", d.ntaps);
   ALDM_REQUIRE(d.K == d.ntaps * d.Cp, ALDM_E_SHAPE, "gemm: K=%d != ntaps*Cp=%d", d.K, d.ntaps * d.Cp);
   ALDM_REQUIRE(d.Kpad % 64 == 0 && d.Kpad >= d.K, ALDM_E_SHAPE, "gemm: Kpad=%d (K=%d)", d.Kpad, d.K);
   ALDM_REQUIRE(d.N >= 1, ALDM_E_SHAPE, "gemm: N=%d", d.N);
-  ALDM_REQUIRE(d.a_hi && d.a_lo, ALDM_E_ARG, "gemm: null A planes");
+  ALDM_REQUIRE(d.a_hi, ALDM_E_ARG, "gemm: null A plane");      // a_lo == NULL: single-plane activations
   ALDM_REQUIRE(aligned16(d.a_hi) && aligned16(d.a_lo), ALDM_E_ALIGN, "gemm: A planes not 16B aligned");
   ALDM_REQUIRE(d.up == 0 || d.up == 1, ALDM_E_ARG, "gemm: up=%d", d.up);
   ALDM_REQUIRE(d.splitk >= 1 && d.splitk <= d.Kpad / 64, ALDM_E_ARG, "gemm: splitk=%d", d.splitk);
@@ -1298,7 +982,7 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
     ALDM_REQUIRE(!d.rowvec, ALDM_E_UNSUPPORTED, "gemm: GEGLU with rowvec");
   }
   if (d.out_mode == ALDM_OUT_QKV) {
-    ALDM_REQUIRE(d.out2_hi && d.out2_lo && d.n_split > 0 && d.n_split < d.N && d.n_split % d.bn == 0 && d.n_split % 32 == 0,
+    ALDM_REQUIRE(d.out2_hi && d.n_split > 0 && d.n_split < d.N && d.n_split % d.bn == 0 && d.n_split % 32 == 0,
                  ALDM_E_ARG, "gemm: bad QKV split (n_split=%d, N=%d, bn=%d)", d.n_split, d.N, d.bn);
     ALDM_REQUIRE(d.tok_per_batch > 0 && d.ld_t >= d.tok_per_batch && d.act != ALDM_ACT_GEGLU, ALDM_E_ARG,
                  "gemm: bad QKV token layout");
@@ -1306,7 +990,7 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
   if (d.out_mode == ALDM_OUT_F32 || d.out_mode == ALDM_OUT_NCHW) {
     ALDM_REQUIRE(d.out, ALDM_E_ARG, "gemm: null out");
   } else {
-    ALDM_REQUIRE(d.out_hi && d.out_lo, ALDM_E_ARG, "gemm: null out planes");
+    ALDM_REQUIRE(d.out_hi, ALDM_E_ARG, "gemm: null out plane");      // out_lo == NULL: single-plane output
     ALDM_REQUIRE(!d.accumulate, ALDM_E_UNSUPPORTED, "gemm: accumulate into planes");
   }
   if ((d.impl & 0xff) == ALDM_GEMM_SIMT) {
@@ -1320,15 +1004,8 @@ int gemm_launch(const aldm_gemm_desc& d, cudaStream_t st) {
     return ALDM_OK;
   }
   ALDM_REQUIRE(d.w_packed && aligned16(d.w_packed), ALDM_E_ARG, "gemm: w_packed null/unaligned");
-  if ((d.impl & 0xff) == ALDM_GEMM_TC_V1) {
-    switch (d.bn) {
-      case 128: return launch_tc<128>(d, M, st);
-      case 64: return launch_tc<64>(d, M, st);
-      default: return launch_tc<32>(d, M, st);
-    }
-  }
+  // ALDM_GEMM_TC_V1 (the round-1 one-tile-per-CTA kernel) is retired: the value selects the persistent kernel
   switch (d.bn) {
-    case 256: return launch_tc2<256>(d, M, st);
     case 128: return launch_tc2<128>(d, M, st);
     case 64: return launch_tc2<64>(d, M, st);
     default: return launch_tc2<32>(d, M, st);

@@ -1,5 +1,5 @@
 // K3: operand preparation -- GroupNorm / LayerNorm / SiLU / leaky-ReLU applied once per tensor and
-// written as the two bf16 planes (hi, lo) the tensor-core GEMM consumes.  All kernels are
+// written as the fp16 operand plane(s) the tensor-core GEMM consumes (hi, and lo unless out_lo == NULL).  All kernels are
 // HBM/L2-bound streaming kernels: float4 loads, 8/16-byte stores, warp-shuffle reductions.
 //
 //   GN  : gn_stats_kernel  (per-block fp32 partial sums -> double partials, no atomics, deterministic)
@@ -64,12 +64,13 @@ __global__ void gn_stats_kernel(const __grid_constant__ aldm_prep_desc d, int nb
   }
 }
 
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* hp, __nv_bfloat16* lp, const float* y) {
+// hp / lp: plane bases (lp may be NULL: single-plane operand), off: element offset
+__device__ __forceinline__ void store_planes4(aldm_plane_t* hp, aldm_plane_t* lp, long long off, const float* y) {
   uint2 h, l;
   split2(y[0], y[1], h.x, l.x);
   split2(y[2], y[3], h.y, l.y);
-  *reinterpret_cast<uint2*>(hp) = h;
-  *reinterpret_cast<uint2*>(lp) = l;
+  *reinterpret_cast<uint2*>(hp + off) = h;
+  if (lp) *reinterpret_cast<uint2*>(lp + off) = l;
 }
 
 // grid (nblk_apply, B); block 256
@@ -104,8 +105,8 @@ __global__ void gn_apply_kernel(const __grid_constant__ aldm_prep_desc d, int nb
   const int r0 = blockIdx.x * rows_per;
   const int r1 = min(d.HW, r0 + rows_per);
   const long long total = (long long)max(0, r1 - r0) * Q;
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
-  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+  aldm_plane_t* hi = reinterpret_cast<aldm_plane_t*>(d.out_hi);
+  aldm_plane_t* lo = reinterpret_cast<aldm_plane_t*>(d.out_lo);
   const bool act = d.mode == ALDM_PREP_GN_SILU;
   for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int pr = (int)(idx / Q), q = (int)(idx % Q);
@@ -117,7 +118,7 @@ __global__ void gn_apply_kernel(const __grid_constant__ aldm_prep_desc d, int nb
       y[e] = fmaf(y[e], s_scale[q * 4 + e], s_shift[q * 4 + e]);
       if (act) y[e] = silu_f(y[e]);
     }
-    store_planes4(hi + row * d.Cp + q * 4, lo + row * d.Cp + q * 4, y);
+    store_planes4(hi, lo, row * d.Cp + q * 4, y);
   }
 }
 
@@ -156,8 +157,8 @@ __global__ void ln_kernel(const __grid_constant__ aldm_prep_desc d) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   const float rstd = rsqrtf(s2 / C + d.eps);
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
-  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+  aldm_plane_t* hi = reinterpret_cast<aldm_plane_t*>(d.out_hi);
+  aldm_plane_t* lo = reinterpret_cast<aldm_plane_t*>(d.out_lo);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int q = lane + 32 * i;
@@ -169,7 +170,7 @@ __global__ void ln_kernel(const __grid_constant__ aldm_prep_desc d) {
       y[1] = (v[i].y - mean) * rstd * g.y + be.y;
       y[2] = (v[i].z - mean) * rstd * g.z + be.z;
       y[3] = (v[i].w - mean) * rstd * g.w + be.w;
-      store_planes4(hi + row * d.Cp + q * 4, lo + row * d.Cp + q * 4, y);
+      store_planes4(hi, lo, row * d.Cp + q * 4, y);
     }
   }
 }
@@ -210,8 +211,8 @@ __global__ void ew_kernel(const __grid_constant__ aldm_prep_desc d) {
   pdl_launch();
   uint4 h, l;
   split8(y, h, l);
-  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.out_hi) + row * d.Cp + c) = h;
-  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.out_lo) + row * d.Cp + c) = l;
+  *reinterpret_cast<uint4*>(reinterpret_cast<aldm_plane_t*>(d.out_hi) + row * d.Cp + c) = h;
+  if (d.out_lo) *reinterpret_cast<uint4*>(reinterpret_cast<aldm_plane_t*>(d.out_lo) + row * d.Cp + c) = l;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -269,8 +270,8 @@ __global__ void gn_apply_col_kernel(const __grid_constant__ aldm_prep_desc d, in
   __syncthreads();
   const int rows_per = (d.HW + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * rows_per, r1 = min(d.HW, r0 + rows_per);
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
-  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+  aldm_plane_t* hi = reinterpret_cast<aldm_plane_t*>(d.out_hi);
+  aldm_plane_t* lo = reinterpret_cast<aldm_plane_t*>(d.out_lo);
   const bool act = d.mode == ALDM_PREP_GN_SILU;
   for (int q = threadIdx.x; q < Q; q += blockDim.x) {
     const int g = (q * 4) / cpg;
@@ -287,96 +288,17 @@ __global__ void gn_apply_col_kernel(const __grid_constant__ aldm_prep_desc d, in
 #pragma unroll
         for (int e = 0; e < 4; ++e) y[e] = silu_f(y[e]);
       }
-      store_planes4(hi + row * d.Cp + q * 4, lo + row * d.Cp + q * 4, y);
+      store_planes4(hi, lo, row * d.Cp + q * 4, y);
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (off unless ALDM_GN_FUSED=1; not yet validated on hardware): statistics and
-// apply in ONE launch.  A block owns G consecutive groups of one sample, walks its [HW x G*cpg] slice twice
-// (second pass out of L2) and needs no scratch round trip.  Motivation: the step's launch list has 186
-// GroupNorm launches of 12-15 us for tensors of a few MB; at the 64..1024-pixel levels both kernels are
-// launch-latency-bound.  Thread mapping: tid -> (row lane, channel quad) with the quad fixed per thread, so a
-// thread accumulates for exactly one group.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_fused_kernel(const __grid_constant__ aldm_prep_desc d, int G) {
-  pdl_wait();
-  __shared__ double s_sum[8], s_sq[8];
-  __shared__ float s_mean[8], s_rstd[8];
-  const int b = blockIdx.y;
-  const int C = d.c0 + d.c1, cpg = C / d.groups, qpg = cpg >> 2;
-  const int qn = G * qpg;                       // channel quads per row owned by this block
-  const int c_base = blockIdx.x * G * cpg;
-  const int R = blockDim.x / qn;                // row lanes
-  const int rl = threadIdx.x / qn, q = threadIdx.x - rl * qn;
-  const bool active = rl < R;
-  if (threadIdx.x < 8) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
-  __syncthreads();
-  const int c = c_base + q * 4;
-  if (active) {
-    float a = 0.f, a2 = 0.f;
-    for (int r = rl; r < d.HW; r += R) {
-      const float4 v = load_cat4(d, (long long)b * d.HW + r, c);
-      a += (v.x + v.y) + (v.z + v.w);
-      a2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, a2))));
-    }
-    atomicAdd(&s_sum[q / qpg], (double)a);
-    atomicAdd(&s_sq[q / qpg], (double)a2);
-  }
-  __syncthreads();
-  if (threadIdx.x < G) {
-    const double n = (double)d.HW * cpg;
-    const double mean = s_sum[threadIdx.x] / n;
-    double var = s_sq[threadIdx.x] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)d.eps));
-  }
-  __syncthreads();
-  if (active) {
-    const float4 ga = *reinterpret_cast<const float4*>(d.gamma + c);
-    const float4 be = *reinterpret_cast<const float4*>(d.beta + c);
-    const float rs = s_rstd[q / qpg], mu = s_mean[q / qpg];
-    const float sc[4] = {rs * ga.x, rs * ga.y, rs * ga.z, rs * ga.w};
-    const float sh[4] = {be.x - mu * sc[0], be.y - mu * sc[1], be.z - mu * sc[2], be.w - mu * sc[3]};
-    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
-    __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
-    const bool act = d.mode == ALDM_PREP_GN_SILU;
-    for (int r = rl; r < d.HW; r += R) {
-      const long long row = (long long)b * d.HW + r;
-      const float4 v = load_cat4(d, row, c);
-      float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
-      if (act) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) y[e] = silu_f(y[e]);
-      }
-      store_planes4(hi + row * d.Cp + c, lo + row * d.Cp + c, y);
-    }
-  }
-  pdl_launch();
-}
-
-static bool gn_fused_enabled() {
-  static const bool on = [] { const char* e = getenv("ALDM_GN_FUSED"); return e && e[0] == '1'; }();
-  return on;
-}
-// groups per block of the fused kernel, or 0 if the shape is not eligible
-static int gn_fused_groups(const aldm_prep_desc& d) {
-  const int C = d.c0 + d.c1, cpg = C / d.groups;
-  if (!gn_fused_enabled() || cpg % 4 != 0 || d.HW > 4096) return 0;
-  int G = d.HW <= 1024 ? 4 : 2;
-  while (G > 1 && (d.groups % G != 0 || G * (cpg / 4) > 256)) G >>= 1;
-  return (G * (cpg / 4) <= 256 && G <= 8) ? G : 0;
 }
 
 int prep_num_launches(const aldm_prep_desc& d) {
-  if (d.mode != ALDM_PREP_GN && d.mode != ALDM_PREP_GN_SILU) return 1;
-  return (d.groups > 0 && (d.c0 + d.c1) % d.groups == 0 && gn_fused_groups(d)) ? 1 : 2;
+  return (d.mode == ALDM_PREP_GN || d.mode == ALDM_PREP_GN_SILU) ? 2 : 1;      // statistics + apply
 }
 
 int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
-  ALDM_REQUIRE(d.src0 && d.out_hi && d.out_lo, ALDM_E_ARG, "prep: null pointer");
+  ALDM_REQUIRE(d.src0 && d.out_hi, ALDM_E_ARG, "prep: null pointer");        // out_lo == NULL: single-plane output
   ALDM_REQUIRE(d.rows > 0 && d.c0 > 0 && d.c1 >= 0, ALDM_E_SHAPE, "prep: rows=%d c0=%d c1=%d", d.rows, d.c0, d.c1);
   const int C = d.c0 + d.c1;
   ALDM_REQUIRE(d.Cp % 8 == 0 && d.Cp >= C && d.Cp < C + 8, ALDM_E_SHAPE, "prep: Cp=%d for C=%d", d.Cp, C);
@@ -388,10 +310,7 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
     ALDM_REQUIRE(d.rows == d.B * d.HW, ALDM_E_SHAPE, "prep GN: rows != B*HW");
     ALDM_REQUIRE(!d.src_nchw, ALDM_E_UNSUPPORTED, "prep GN: NCHW source");
     const int cpg = C / d.groups;
-    if (const int G = gn_fused_groups(d)) {
-      ALDM_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(d.groups / G, d.B), dim3(256), 0, st, d, G));
-      ALDM_CHECK_CUDA(cudaGetLastError());
-    } else if (cpg % 4 == 0) {
+    if (cpg % 4 == 0) {
       // column-owner kernels: ~8 rows per block so that even the 64-pixel level fills the machine
       int nblk = cdiv(d.HW, 8);
       if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;

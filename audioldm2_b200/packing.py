@@ -4,10 +4,11 @@ Layout consumed by csrc/gemm.cu (and produced on-device by pack_b_kernel for dyn
 
     packed[n_tile][k_blk][plane(hi,lo)][row r in 0..bn)[128 bytes]
 
-where a row holds 64 bf16 K-elements of output channel ``n_tile*bn + r`` and its eight 16-byte
+where a row holds 64 fp16 K-elements of output channel ``n_tile*bn + r`` and its eight 16-byte
 chunks are XOR-swizzled with ``r & 7`` (the UMMA SWIZZLE_128B K-major canonical layout), so one
-``cp.async.bulk`` per stage drops a ready-to-use B tile into shared memory.  ``hi = bf16(w)``,
-``lo = bf16(w - hi)``.
+``cp.async.bulk`` per stage drops a ready-to-use B tile into shared memory.  ``hi = fp16(w)``,
+``lo = fp16(w - hi)``: 22 significand bits for |w| >= 2^-14 * 2^11, absolute error <= 2^-25 below
+(fp16 subnormals), i.e. weights are exact to fp32 round-off at the magnitudes networks hold.
 
 K ordering of a convolution is ``k = tap * Cp + c`` (Cp = Cin rounded up to 8, zero padded), taps
 in the order of the (dy, dx) list the planner emits.
@@ -62,9 +63,14 @@ def geglu_row_order(n_inner: int, bn: int) -> torch.Tensor:
     return torch.cat(idx)
 
 
-def split_bf16(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
+F16_MAX = 65504.0
+
+
+def split_f16(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x ~= hi + lo with fp16 planes, saturating at +-65504 exactly like the device-side split (csrc/common.cuh)."""
+    w = w.float().clamp(-F16_MAX, F16_MAX)
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
     return hi, lo
 
 
@@ -74,7 +80,7 @@ def pack_tiles(wm: torch.Tensor, bn: int) -> Tuple[torch.Tensor, torch.Tensor, i
     Npad, Kpad = round_up(N, bn), round_up(K, BK)
     plain = torch.zeros(Npad, Kpad, dtype=torch.float32)
     plain[:N, :K] = wm
-    hi, lo = split_bf16(plain)
+    hi, lo = split_f16(plain)
     nt, kb = Npad // bn, Kpad // BK
 
     def tiles(p: torch.Tensor) -> torch.Tensor:
@@ -95,7 +101,7 @@ def unpack_tiles(packed: torch.Tensor, N: int, K: int, bn: int) -> torch.Tensor:
     """Inverse of pack_tiles (hi + lo as fp32) -- used by tests."""
     Npad, Kpad = round_up(N, bn), round_up(K, BK)
     nt, kb = Npad // bn, Kpad // BK
-    both = packed.view(torch.bfloat16).reshape(nt, kb, 2, bn, 8, 8).float()
+    both = packed.view(torch.float16).reshape(nt, kb, 2, bn, 8, 8).float()
     r = torch.arange(bn) & 7
     j = torch.arange(8)
     src = (j[None, :] ^ r[:, None])

@@ -50,21 +50,21 @@ class F32:            # fp32 activation [rows, C] (channels-last)
 
 
 @dataclass
-class Planes:         # bf16 hi/lo operand planes [rows, Cp]
+class Planes:         # fp16 operand planes [rows, Cp]: hi = fp16(x) and, for two-plane operands, lo = fp16(x - hi)
     hi: Ref
-    lo: Ref
+    lo: Optional[Ref]
     rows: int
     Cp: int
 
     @property
     def nbytes(self):
-        return 2 * self.rows * self.Cp * 2
+        return (1 if self.lo is None else 2) * self.rows * self.Cp * 2
 
 
 @dataclass
 class VT:             # transposed V planes [(b*C + c), ld_t] (keys contiguous), written by an ALDM_OUT_QKV GEMM
     hi: Ref
-    lo: Ref
+    lo: Optional[Ref]
     ld_t: int
 
 
@@ -227,13 +227,14 @@ class Plan:
 
 class Planner:
     def __init__(self, impl: str = "tc", keep_plain: bool = False, splitk: bool = True, n_sm: int = 148):
-        self.impl = {"tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT, "tc1": _lib.GEMM_TC_V1}[impl]
+        self.impl = {"tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT}[impl]
         self.keep_plain = keep_plain or impl == "simt"
         self.use_splitk = splitk and impl != "simt"
         self.static_b = os.environ.get("ALDM_BPRE", "1") != "0"      # weight prefetch ahead of the PDL wait (A/B switch)
-        # EXPERIMENTAL 128 x 256 tiles for N % 256 == 0 (csrc/gemm.cu Tc3Cfg<256>); off until validated on hardware
-        self.bn256 = os.environ.get("ALDM_BN256", "0") == "1" and impl == "tc"
         self.n_sm = n_sm
+        # planes of the token-side operands of the UNet (LayerNorm outputs, Q|K, V^T, attention output, GEGLU output):
+        # 1 = single fp16 plane (default; precision budget in DESIGN.md section 3), 2 = hi + lo everywhere
+        self.tok_planes = 2 if os.environ.get("ALDM_TOKEN_PLANES", "1") == "2" else 1
         self.arena = Arena()
         self.pool = Pool()
         self.ops: List[dict] = []
@@ -253,8 +254,6 @@ class Planner:
         yields >= ~0.8 * n_sm tiles (per-tile time of a short K loop is dominated by fixed latencies, so
         more, narrower tiles in flight win)."""
         cands = [b for b in ((128, 64) if geglu else (128, 64, 32)) if N % b == 0 and b >= min_bn]
-        if self.bn256 and N % 256 == 0 and self._bn256_pays(N, m_rows):
-            cands = [256] + cands
         if not cands:
             return 128 if geglu else packing.choose_bn(N)
         if not m_rows:
@@ -265,17 +264,6 @@ class Planner:
                 return b
         return cands[-1]
 
-    def _bn256_pays(self, N: int, m_rows: Optional[int]) -> bool:
-        """128 x 256 tiles halve the tile count: take them only when that still fills the persistent grid at least
-        (nearly) once and does not lose more than a few percent to wave quantisation against 128 x 128 tiles
-        (e.g. M = 1024, N = 5120: 160 tiles on 148 SMs would run two rounds at 54% -- keep 128 there)."""
-        if not m_rows:
-            return True
-        mt = math.ceil(m_rows / 128)
-        eff = lambda tiles: tiles / (math.ceil(tiles / self.n_sm) * self.n_sm)
-        t256, t128 = mt * (N // 256), mt * (N // 128)
-        return t256 >= int(0.8 * self.n_sm) and eff(t256) >= eff(t128) - 0.03
-
     def wmat(self, wm: torch.Tensor, bias: Optional[torch.Tensor], ntaps: int, cp: int, geglu: bool = False,
              bn: Optional[int] = None, m_rows: Optional[int] = None) -> WMat:
         N, K = wm.shape
@@ -284,8 +272,6 @@ class Planner:
         # (more CTAs re-read the same activation rows, MMA N=32/64 is less efficient), so the widest tile
         # that divides N is always used; m_rows is kept for future tuning.
         narrow = int(os.environ.get("ALDM_NARROW", "0"))       # experiment switch: smallest N tile the heuristic may pick
-        if bn is None and self.bn256 and N % 256 == 0 and not narrow:
-            bn = 256 if self._bn256_pays(N, m_rows) else None
         bn = bn or self.bn_for_rows(N, m_rows if narrow else None, geglu, min_bn=narrow or 32)
         if geglu:
             order = packing.geglu_row_order(N // 2, bn)
@@ -301,7 +287,7 @@ class Planner:
                     bref, N, K, Kpad, bn, cp, ntaps)
 
     def bn_for_split(self, N: int, n_split: int) -> int:
-        for b in ((256,) if self.bn256 else ()) + (128, 64, 32):
+        for b in (128, 64, 32):
             if n_split % b == 0 and N % b == 0:
                 return b
         raise ValueError((N, n_split))
@@ -315,19 +301,21 @@ class Planner:
     def f32(self, rows: int, Cc: int) -> F32:
         return F32(Ref("ws", self.pool.alloc(rows * Cc * 4)), rows, Cc)
 
-    def planes(self, rows: int, Cc: int) -> Planes:
+    def planes(self, rows: int, Cc: int, n: int = 2) -> Planes:
+        """n = 2: hi + lo (22-bit operands, three tensor-core passes); n = 1: hi only (11-bit activations against 22-bit
+        weights, two passes) -- the token-side operands of the UNet."""
         cp = round_up(Cc, 8)
-        off = self.pool.alloc(2 * rows * cp * 2)
-        return Planes(Ref("ws", off), Ref("ws", off + rows * cp * 2), rows, cp)
+        off = self.pool.alloc(n * rows * cp * 2)
+        return Planes(Ref("ws", off), Ref("ws", off + rows * cp * 2) if n == 2 else None, rows, cp)
 
     def raw(self, nbytes: int) -> Ref:
         return Ref("ws", self.pool.alloc(nbytes))
 
-    def vt(self, batch: int, Cc: int, ntok: int) -> VT:
+    def vt(self, batch: int, Cc: int, ntok: int, n: int = 2) -> VT:
         ld_t = round_up(ntok, 8)
-        n = batch * Cc * ld_t * 2
-        off = self.pool.alloc(2 * n)
-        return VT(Ref("ws", off), Ref("ws", off + n), ld_t)
+        nb = batch * Cc * ld_t * 2
+        off = self.pool.alloc(n * nb)
+        return VT(Ref("ws", off), Ref("ws", off + nb) if n == 2 else None, ld_t)
 
     def attn(self, q: Planes, q_col: int, k: Planes, k_col: int, vt: VT, out: Planes, *, B: int, heads: int, Nq: int,
              Nk: int, mask: Optional[Ref], scale: float, kv_bmod: int = 0):
@@ -355,9 +343,9 @@ class Planner:
 
     def prep(self, mode: int, src0: F32, src1: Optional[F32] = None, gamma: Optional[Ref] = None,
              beta: Optional[Ref] = None, eps: float = 0.0, slope: float = 0.0, B: int = 0, HW: int = 0,
-             src_nchw: bool = False, out: Optional[Planes] = None) -> Planes:
+             src_nchw: bool = False, out: Optional[Planes] = None, n: int = 2) -> Planes:
         Cc = src0.C + (src1.C if src1 is not None else 0)
-        out = out or self.planes(src0.rows, Cc)
+        out = out or self.planes(src0.rows, Cc, n)
         self.ops.append(dict(kind="prep", tag=self.tag, src0=src0.ref, src1=src1.ref if src1 is not None else None,
                              gamma=gamma, beta=beta, out_hi=out.hi, out_lo=out.lo,
                              scratch=self._gn_scratch(B) if mode in (_lib.PREP_GN, _lib.PREP_GN_SILU) else None,
@@ -378,7 +366,8 @@ class Planner:
         assert len(taps) == w.ntaps and a.Cp == w.Cp, (len(taps), w.ntaps, a.Cp, w.Cp)
         M = B * OH * OW
         n_out = w.N // 2 if act == _lib.ACT_GEGLU else w.N
-        o = dict(kind="gemm", tag=self.tag, a_hi=a.hi + a_off_rows * a.Cp * 2, a_lo=a.lo + a_off_rows * a.Cp * 2,
+        o = dict(kind="gemm", tag=self.tag, a_hi=a.hi + a_off_rows * a.Cp * 2,
+                 a_lo=(a.lo + a_off_rows * a.Cp * 2) if a.lo is not None else None,
                  w_packed=w.packed, w_plain=w.plain, bias=w.bias if use_bias else None, rowvec=rowvec,
                  res=(res.ref if res is not None else res_ref), out=None, out_hi=None, out_lo=None, ws=None,
                  B=B, H=H, W=W, Cp=a.Cp, up=up, bmod=bmod, OH=OH, OW=OW, sy=sy, sx=sx, ntaps=w.ntaps,
@@ -455,6 +444,7 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
     (rows [0,B_l) with the unconditional, [B_l,2B_l) with the conditional conditioning) from one copy
     of x, replacing the two separate apply_model calls of ddim.py:293-296."""
     P = Planner(**pk)
+    TP = P.tok_planes
     spec = arch.unet_spec(cfg)
     Cin, T, Fq = latent
     Bl = batch
@@ -504,8 +494,8 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
                     wm, taps, cp = packing.conv_weight_matrix(wkv)
                     w = P.wmat(wm, None, taps, cp, bn=P.bn_for_split(2 * l.cin, l.cin))
                     cb, L = ctx_bufs[l.ctx_slot]
-                    kpl = P.planes(Bt * L, l.cin)                                   # persistent (step-invariant)
-                    vtp = P.vt(Bt, l.cin, L)
+                    kpl = P.planes(Bt * L, l.cin, TP)                               # persistent (step-invariant)
+                    vtp = P.vt(Bt, l.cin, L, TP)
                     P.gemm(ctx_planes[l.ctx_slot], w, B=1, H=Bt * L, qkv=(kpl, vtp, l.cin, L))
                     kv_cache[n] = (kpl, vtp, L)
     if film is not None:
@@ -563,21 +553,21 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
     def attention(nm: str, h: F32, norm: str, heads: int, Cc: int, HW: int, kv, mask: Optional[Ref]) -> F32:
         """x = attn(LN(x)) + x  (attention.py:343-367, 406-409).  The projection GEMMs write Q|K as operand
         planes and V transposed (ALDM_OUT_QKV), which is what the tcgen05 attention kernel consumes."""
-        p = P.prep(_lib.PREP_LN, h, None, P.vec(sd[norm + ".weight"]), P.vec(sd[norm + ".bias"]), eps=1e-5)
-        ao = P.planes(h.rows, Cc)
+        p = P.prep(_lib.PREP_LN, h, None, P.vec(sd[norm + ".weight"]), P.vec(sd[norm + ".bias"]), eps=1e-5, n=TP)
+        ao = P.planes(h.rows, Cc, TP)
         scale = (Cc // heads) ** -0.5
         if kv is None:
             wq = torch.cat([sd[nm + ".to_q.weight"], sd[nm + ".to_k.weight"], sd[nm + ".to_v.weight"]], 0).float()
             wm, taps, cp = packing.conv_weight_matrix(wq)
-            qk = P.planes(h.rows, 2 * Cc)
-            vtp = P.vt(Bt, Cc, HW)
+            qk = P.planes(h.rows, 2 * Cc, TP)
+            vtp = P.vt(Bt, Cc, HW, TP)
             P.gemm(p, P.wmat(wm, None, taps, cp, bn=P.bn_for_split(3 * Cc, 2 * Cc)), B=1, H=h.rows, qkv=(qk, vtp, 2 * Cc, HW))
             P.free(p)
             P.attn(qk, 0, qk, Cc, vtp, ao, B=Bt, heads=heads, Nq=HW, Nk=HW, mask=None, scale=scale)
             P.free(qk, vtp)
         else:
             kpl, vtp, L = kv
-            q = P.planes(h.rows, Cc)
+            q = P.planes(h.rows, Cc, TP)
             P.gemm(p, P.conv_w(sd, nm + ".to_q", m_rows=h.rows), B=1, H=h.rows, out_planes=q)
             P.free(p)
             P.attn(q, 0, kpl, 0, vtp, ao, B=Bt, heads=heads, Nq=HW, Nk=L, mask=mask, scale=scale)
@@ -600,10 +590,10 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
             kv = kv_cache.get(b + ".attn2") if l.ctx_slot >= 0 else None
             h2 = attention(b + ".attn2", h, b + ".norm2", l.heads, Cc, HW, kv,
                            mask_refs[l.ctx_slot] if l.ctx_slot >= 0 else None); P.free(h); h = h2
-            p = P.prep(_lib.PREP_LN, h, None, P.vec(sd[b + ".norm3.weight"]), P.vec(sd[b + ".norm3.bias"]), eps=1e-5)
+            p = P.prep(_lib.PREP_LN, h, None, P.vec(sd[b + ".norm3.weight"]), P.vec(sd[b + ".norm3.bias"]), eps=1e-5, n=TP)
             wff = sd[b + ".ff.net.0.proj.weight"].float()
             wm, taps, cp = packing.conv_weight_matrix(wff)
-            g = P.planes(h.rows, 4 * Cc)
+            g = P.planes(h.rows, 4 * Cc, TP)
             P.gemm(p, P.wmat(wm, sd[b + ".ff.net.0.proj.bias"], taps, cp, geglu=True, m_rows=h.rows), B=1, H=h.rows, out_planes=g,
                    act=_lib.ACT_GEGLU)
             P.free(p)

@@ -20,7 +20,8 @@ while [ $# -gt 0 ]; do
       echo "== tests rc=$?"; tail -5 gpurun_out/pytest_$TAG.log ;;
     sweep)
       : > gpurun_out/sweep_$TAG.jsonl
-      for cfg in "1:" "2:" "4:" "2:ALDM_GN_FUSED=1" "2:ALDM_BN256=1" "2:ALDM_GN_FUSED=1 ALDM_BN256=1" "4:ALDM_GN_FUSED=1"; do
+      IFS=';' read -ra CFGS <<< "${SWEEP:-1:ALDM_TOKEN_PLANES=1;1:ALDM_TOKEN_PLANES=2}"      # "lanes:ENV=.. ENV=..;..."
+      for cfg in "${CFGS[@]}"; do
         lanes=${cfg%%:*}; sw=${cfg#*:}
         env $sw timeout 300 python scripts/step_time.py --lanes $lanes --tag "lanes$lanes $sw" 2>gpurun_out/sweep_err.log | grep '^{' >> gpurun_out/sweep_$TAG.jsonl || tail -3 gpurun_out/sweep_err.log
       done
@@ -31,6 +32,14 @@ while [ $# -gt 0 ]; do
     refarm)
       timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1
       echo "== reference arm rc=$?"; tail -c 1200 gpurun_out/bench_ref_$TAG.log ;;
+    ops)
+      for pl in 1 2; do timeout 600 python scripts/prof_ops.py --reps 40 --planes $pl > gpurun_out/prof_ops_${TAG}_p$pl.txt 2>&1; echo "== prof_ops planes=$pl"; cat gpurun_out/prof_ops_${TAG}_p$pl.txt; done ;;
+    optests)
+      timeout 1200 python -m pytest tests/test_gpu_ops.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_ops_$TAG.log 2>&1
+      echo "== op tests rc=$?"; tail -15 gpurun_out/pytest_ops_$TAG.log ;;
+    nettests)
+      timeout 1500 python -m pytest tests/test_gpu_nets.py tests/test_gpu_zz_engine_abi.py -m gpu -q -s -p no:cacheprovider > gpurun_out/pytest_nets_$TAG.log 2>&1
+      echo "== net tests rc=$?"; grep "rel L2\|passed\|failed\|FAILED\|Error" gpurun_out/pytest_nets_$TAG.log | tail -60 ;;
     ncu-list)
       timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
         --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 0 --ddim-steps 2 --no-graph --no-cpu-baseline \

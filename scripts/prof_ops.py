@@ -39,8 +39,12 @@ CASES = {
 }
 
 
+TOK = 1      # planes of the token-side operands (--planes)
+
+
 def build(name, impl):
     kind, p = CASES[name]
+    tok = TOK if name.startswith(("lin_", "ln_")) else 2
     g = torch.Generator().manual_seed(0)
     P = Planner(impl=impl)
     ios, ins = {}, {}
@@ -48,18 +52,18 @@ def build(name, impl):
     if kind == "gemm":
         B, H, W, Cin, N, taps = p["B"], p["H"], p["W"], p["Cin"], p["N"], p["taps"]
         src = F32(P.raw(B * H * W * Cin * 4), B * H * W, Cin)
-        a = P.prep(_lib.PREP_COPY, src)
+        a = P.prep(_lib.PREP_COPY, src, n=tok)
         first = len(P.ops)
         wm = torch.randn(N, len(taps) * Cin, generator=g) / math.sqrt(len(taps) * Cin)
         M = B * H * W
         kw = dict(B=B, H=H, W=W, taps=taps)
         if p.get("geglu"):
             w = P.wmat(wm, torch.zeros(N), len(taps), Cin, geglu=True)
-            P.gemm(a, w, out_planes=P.planes(M, N // 2), act=_lib.ACT_GEGLU, **kw)
+            P.gemm(a, w, out_planes=P.planes(M, N // 2, tok), act=_lib.ACT_GEGLU, **kw)
         elif p.get("qkv"):
             Cc = N // 3
             w = P.wmat(wm, None, len(taps), Cin, bn=P.bn_for_split(N, 2 * Cc))
-            P.gemm(a, w, qkv=(P.planes(M, 2 * Cc), P.vt(M // p["qkv"], Cc, p["qkv"]), 2 * Cc, p["qkv"]), **kw)
+            P.gemm(a, w, qkv=(P.planes(M, 2 * Cc, tok), P.vt(M // p["qkv"], Cc, p["qkv"], tok), 2 * Cc, p["qkv"]), **kw)
         else:
             w = P.wmat(wm, torch.zeros(N), len(taps), Cin)
             r = P.f32(M, N) if p.get("res") else None
@@ -72,10 +76,10 @@ def build(name, impl):
         B, h, N = p["B"], p["heads"], p["N"]
         Cc = h * 32
         src = F32(P.raw(B * N * 2 * Cc * 4), B * N, 2 * Cc)
-        qk = P.prep(_lib.PREP_COPY, src)
-        vt = P.vt(B, Cc, N)
+        qk = P.prep(_lib.PREP_COPY, src, n=1)
+        vt = P.vt(B, Cc, N, 1)
         first = len(P.ops)
-        P.attn(qk, 0, qk, Cc, vt, P.planes(B * N, Cc), B=B, heads=h, Nq=N, Nk=N, mask=None, scale=32 ** -0.5)
+        P.attn(qk, 0, qk, Cc, vt, P.planes(B * N, Cc, 1), B=B, heads=h, Nq=N, Nk=N, mask=None, scale=32 ** -0.5)
         ios["src"] = ("f32", src.ref, (B * N, 2 * Cc)); ins["src"] = torch.randn(B * N, 2 * Cc, generator=g)
         flops = 4.0 * B * h * N * N * 32
     else:
@@ -83,7 +87,7 @@ def build(name, impl):
         src = F32(P.raw(rows * Cc * 4), rows, Cc)
         first = len(P.ops)
         gam, bet = P.vec(torch.ones(Cc)), P.vec(torch.zeros(Cc))
-        P.prep(p["mode"], src, None, gam, bet, eps=1e-5, B=p.get("B", 0), HW=rows // max(1, p.get("B", 1)))
+        P.prep(p["mode"], src, None, gam, bet, eps=1e-5, B=p.get("B", 0), HW=rows // max(1, p.get("B", 1)), n=tok)
         ios["src"] = ("f32", src.ref, (rows, Cc)); ins["src"] = torch.randn(rows, Cc, generator=g)
         flops = 0.0
     pl = P.finish(ios)
@@ -95,8 +99,11 @@ def main():
     ap.add_argument("--reps", type=int, default=40)
     ap.add_argument("--only", default=None)
     ap.add_argument("--impl", default="tc")
+    ap.add_argument("--planes", type=int, default=1, help="planes of the token-side operands (lin_* / ln_* cases)")
     ap.add_argument("--dbg", type=int, default=0, help="GEMM profiling aid bits: 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue")
     a = ap.parse_args()
+    global TOK
+    TOK = a.planes
     dev = torch.device("cuda:0")
     print(f"{'case':28s} {'us/launch':>10s} {'TFLOP/s':>9s}")
     for name in CASES:

@@ -2,7 +2,8 @@
 
 Executes the planner IR (audioldm2_b200/plan.py) op by op with torch on byte buffers that stand
 in for the device arena / workspace.  Semantics follow include/aldm_b200.h; arithmetic is plain
-fp32 (operand planes are emulated as hi+lo bf16 pairs exactly like the kernels split them), so a
+fp32 (operand planes are emulated as fp16 hi [+ lo] exactly like the kernels split them; a missing lo plane
+-- ``None`` -- is a single-plane operand), so a
 run checks graph wiring, weight layout / K ordering, epilogue flags and the plan-time buffer
 allocator (a liveness bug corrupts the result) -- everything except the CUDA kernels themselves.
 """
@@ -29,8 +30,8 @@ class Emulator:
     def f32(self, ref: Ref, n: int) -> torch.Tensor:
         return self.mem[ref.region][ref.off:ref.off + 4 * n].view(torch.float32)
 
-    def bf16(self, ref: Ref, n: int) -> torch.Tensor:
-        return self.mem[ref.region][ref.off:ref.off + 2 * n].view(torch.bfloat16)
+    def f16(self, ref: Ref, n: int) -> torch.Tensor:
+        return self.mem[ref.region][ref.off:ref.off + 2 * n].view(torch.float16)
 
     def i64(self, ref: Ref, n: int) -> torch.Tensor:
         return self.mem[ref.region][ref.off:ref.off + 8 * n].view(torch.int64)
@@ -48,16 +49,31 @@ class Emulator:
         kind, ref, shape = self.plan.io[name]
         return self.f32(ref, int(np.prod(shape))).reshape(shape).clone()
 
-    def write_planes(self, hi: Ref, lo: Ref, x: torch.Tensor, ld: int, rows: int, col0: int = 0):
-        h = x.to(torch.bfloat16)
-        l = (x - h.float()).to(torch.bfloat16)
-        H = self.bf16(hi, rows * ld).reshape(rows, ld)
-        L = self.bf16(lo, rows * ld).reshape(rows, ld)
+    def write_planes(self, hi: Ref, lo, x: torch.Tensor, ld: int, rows: int, col0: int = 0):
+        h, l = packing.split_f16(x)
+        H = self.f16(hi, rows * ld).reshape(rows, ld)
         H[:, col0:col0 + x.shape[1]] = h
-        L[:, col0:col0 + x.shape[1]] = l
+        if lo is not None:
+            L = self.f16(lo, rows * ld).reshape(rows, ld)
+            L[:, col0:col0 + x.shape[1]] = l
 
-    def read_planes(self, hi: Ref, lo: Ref, rows: int, ld: int) -> torch.Tensor:
-        return self.bf16(hi, rows * ld).reshape(rows, ld).float() + self.bf16(lo, rows * ld).reshape(rows, ld).float()
+    def read_planes(self, hi: Ref, lo, rows: int, ld: int) -> torch.Tensor:
+        x = self.f16(hi, rows * ld).reshape(rows, ld).float()
+        return x if lo is None else x + self.f16(lo, rows * ld).reshape(rows, ld).float()
+
+    def strided_planes(self, hi: Ref, lo, rows: int, cols: int, ld: int):
+        """(hi, lo-or-None) fp16 views [rows, cols] with row stride ld"""
+        n = (rows - 1) * ld + cols
+        H = torch.as_strided(self.f16(hi, n), (rows, cols), (ld, 1))
+        L = None if lo is None else torch.as_strided(self.f16(lo, n), (rows, cols), (ld, 1))
+        return H, L
+
+    def put_planes(self, hi: Ref, lo, rows: int, cols: int, ld: int, idx, v: torch.Tensor):
+        h, l = packing.split_f16(v)
+        H, L = self.strided_planes(hi, lo, rows, cols, ld)
+        H[idx] = h
+        if L is not None:
+            L[idx] = l
 
     # ---- ops -----------------------------------------------------------------------------
     def run(self, first: int = 0, last=None):
@@ -74,7 +90,7 @@ class Emulator:
         freqs = self.f32(o["freqs"], dim // 2)
         args = t[:, None] * freqs[None]
         emb = torch.cat([torch.cos(args), torch.sin(args)], -1)
-        self.write_planes(o["out_hi"], o["out_lo"], emb, dim, B)
+        self.write_planes(o["out_hi"], o.get("out_lo"), emb, dim, B)
 
     def op_prep(self, o):
         rows, c0, c1, Cp, mode = o["rows"], o["c0"], o["c1"], o["Cp"], o["mode"]
@@ -104,7 +120,7 @@ class Emulator:
             y = x
         if Cp > Cc:
             y = torch.cat([y, torch.zeros(rows, Cp - Cc)], 1)
-        self.write_planes(o["out_hi"], o["out_lo"], y, Cp, rows)
+        self.write_planes(o["out_hi"], o.get("out_lo"), y, Cp, rows)
 
     def op_packb(self, o):
         N, K, bn, lds = o["N"], o["K"], o["bn"], o["lds"]
@@ -120,7 +136,7 @@ class Emulator:
     def op_softmax(self, o):
         rows, n = o["rows"], o["n"]
         x = self.f32(o["x"], rows * n).reshape(rows, n) * o["scale"]
-        self.write_planes(o["out_hi"], o["out_lo"], F.softmax(x, -1), n, rows)
+        self.write_planes(o["out_hi"], o.get("out_lo"), F.softmax(x, -1), n, rows)
 
     def op_attn(self, o):
         B, h, Nq, Nk = o["B"], o["heads"], o["Nq"], o["Nk"]
@@ -129,16 +145,15 @@ class Emulator:
         bmod = o["kv_bmod"]
         Bkv = bmod if bmod > 0 else B
 
-        def planes(hi, lo, rows, ld, col):
+        def planes(hi, rows, ld, col):       # the attention op reads the hi plane only (single-plane fp16 Q, K, V)
             n = (rows - 1) * ld + col + Cc
-            full = self.bf16(hi, n).float() + self.bf16(lo, n).float()
-            return torch.as_strided(full, (rows, Cc), (ld, 1), col)
+            return torch.as_strided(self.f16(hi, n).float(), (rows, Cc), (ld, 1), col)
 
-        q = planes(o["q_hi"], o["q_lo"], B * Nq, o["ldq"], o["q_col"]).reshape(B, Nq, h, d).permute(0, 2, 1, 3)
-        k = planes(o["k_hi"], o["k_lo"], Bkv * Nk, o["ldk"], o["k_col"]).reshape(Bkv, Nk, h, d).permute(0, 2, 1, 3)
+        q = planes(o["q_hi"], B * Nq, o["ldq"], o["q_col"]).reshape(B, Nq, h, d).permute(0, 2, 1, 3)
+        k = planes(o["k_hi"], Bkv * Nk, o["ldk"], o["k_col"]).reshape(Bkv, Nk, h, d).permute(0, 2, 1, 3)
         ld_t = o["ld_t"]
         nvt = Bkv * Cc * ld_t
-        vt = (self.bf16(o["vt_hi"], nvt).float() + self.bf16(o["vt_lo"], nvt).float()).reshape(Bkv, h, d, ld_t)[..., :Nk]
+        vt = self.f16(o["vt_hi"], nvt).float().reshape(Bkv, h, d, ld_t)[..., :Nk]
         v = vt.permute(0, 1, 3, 2)                                  # [Bkv, h, Nk, d]
         if bmod > 0:
             idx = torch.arange(B) % bmod
@@ -150,8 +165,11 @@ class Emulator:
             if bmod > 0:
                 m = m[torch.arange(B) % bmod]
             sim = sim.masked_fill(~(m == 1), -torch.finfo(torch.float32).max)
-        out = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), v).permute(0, 2, 1, 3).reshape(B * Nq, Cc)
-        self.write_planes(o["out_hi"], o["out_lo"], out, o["ldo"], B * Nq)
+        # the kernel rounds the un-normalised probabilities exp(s - max) to fp16 before P V and divides by the fp32 row sum
+        p = torch.exp(sim - sim.amax(-1, keepdim=True))
+        out = torch.einsum("bhij,bhjd->bhid", p.half().float(), v) / p.sum(-1, keepdim=True)
+        out = out.permute(0, 2, 1, 3).reshape(B * Nq, Cc)
+        self.write_planes(o["out_hi"], o.get("out_lo"), out, o["ldo"], B * Nq)
 
     def op_gemm(self, o):
         B, H, W, Cp, up = o["B"], o["H"], o["W"], o["Cp"], o["up"]
@@ -164,7 +182,7 @@ class Emulator:
         Hs, Ws = H >> up, W >> up
         bmod = o["bmod"]
         Bsrc = bmod if bmod > 0 else B
-        A = self.read_planes(o["a_hi"], o["a_lo"], Bsrc * Hs * Ws, Cp).reshape(Bsrc, Hs, Ws, Cp)
+        A = self.read_planes(o["a_hi"], o.get("a_lo"), Bsrc * Hs * Ws, Cp).reshape(Bsrc, Hs, Ws, Cp)
         assert torch.isfinite(A).all(), "gemm reads uninitialised / non-finite operand planes"
         if bmod > 0:
             A = A[torch.arange(B) % bmod]
@@ -223,29 +241,19 @@ class Emulator:
                 v = v + O[orow]
             O[orow] = v
             if o.get("out_hi") is not None:      # dual output (fp32 + operand planes)
-                h = v.to(torch.bfloat16); l = (v - h.float()).to(torch.bfloat16)
-                Hh = torch.as_strided(self.bf16(o["out_hi"], (nrows_out - 1) * ld + n_out), (nrows_out, n_out), (ld, 1))
-                Ll = torch.as_strided(self.bf16(o["out_lo"], (nrows_out - 1) * ld + n_out), (nrows_out, n_out), (ld, 1))
-                Hh[orow] = h; Ll[orow] = l
+                self.put_planes(o["out_hi"], o.get("out_lo"), nrows_out, n_out, ld, orow, v)
         elif mode == _lib.OUT_QKV:
             ns, tpb, ld_t, ld = o["n_split"], o["tok_per_batch"], o["ld_t"], o["ldo"]
-            a = v[:, :ns]
-            h = a.to(torch.bfloat16); l = (a - h.float()).to(torch.bfloat16)
-            Hh = torch.as_strided(self.bf16(o["out_hi"], (M - 1) * ld + ns), (M, ns), (ld, 1))
-            Ll = torch.as_strided(self.bf16(o["out_lo"], (M - 1) * ld + ns), (M, ns), (ld, 1))
-            Hh[:] = h; Ll[:] = l
+            self.put_planes(o["out_hi"], o.get("out_lo"), M, ns, ld, slice(None), v[:, :ns])
             Cv, nb = N - ns, M // tpb
             t = v[:, ns:].reshape(nb, tpb, Cv).permute(0, 2, 1)              # [b, c, tok]
             tp = torch.zeros(nb, Cv, ld_t); tp[:, :, :tpb] = t
-            th = tp.to(torch.bfloat16); tl = (tp - th.float()).to(torch.bfloat16)
-            self.bf16(o["out2_hi"], nb * Cv * ld_t)[:] = th.reshape(-1)
-            self.bf16(o["out2_lo"], nb * Cv * ld_t)[:] = tl.reshape(-1)
+            th, tl = packing.split_f16(tp)
+            self.f16(o["out2_hi"], nb * Cv * ld_t)[:] = th.reshape(-1)
+            if o.get("out2_lo") is not None:
+                self.f16(o["out2_lo"], nb * Cv * ld_t)[:] = tl.reshape(-1)
         elif mode == _lib.OUT_PLANES:
-            ld = o["ldo"]
-            h = v.to(torch.bfloat16); l = (v - h.float()).to(torch.bfloat16)
-            Hh = torch.as_strided(self.bf16(o["out_hi"], (nrows_out - 1) * ld + n_out), (nrows_out, n_out), (ld, 1))
-            Ll = torch.as_strided(self.bf16(o["out_lo"], (nrows_out - 1) * ld + n_out), (nrows_out, n_out), (ld, 1))
-            Hh[orow] = h; Ll[orow] = l
+            self.put_planes(o["out_hi"], o.get("out_lo"), nrows_out, n_out, o["ldo"], orow, v)
         else:   # NCHW
             O = self.f32(o["out"], B * N * OH * OW).reshape(B, N, OH, OW)
             O[:] = v.reshape(B, OH, OW, N).permute(0, 3, 1, 2)

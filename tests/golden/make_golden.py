@@ -119,7 +119,7 @@ class _StubModel:
 
 
 @torch.no_grad()
-def gen_ddim(R, name, cfg, B, S, masked=False, with_audio=False, t5_len=32):
+def gen_ddim(R, name, cfg, B, S, masked=False, with_audio=False, t5_len=32, audio_rows=None):
     m = ref_unet(R, cfg["unet"])
     tables = OF.ddpm_tables(cfg["linear_start"], cfg["linear_end"], cfg["timesteps"])
     stub = _StubModel(m, tables)
@@ -141,8 +141,12 @@ def gen_ddim(R, name, cfg, B, S, masked=False, with_audio=False, t5_len=32):
         h = torch.nn.functional.conv2d(img, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
         mel = dec(h)
         g = ref_vocoder(R, cfg["vocoder"])
+        wave = g(mel.squeeze(1).permute(0, 2, 1))                 # ddpm.py:932-935
+        if audio_rows is not None:       # large batches: keep the fixture small, store mel / waveform of a few rows only
+            out["audio_rows"] = torch.tensor(audio_rows)
+            mel, wave = mel[audio_rows], wave[audio_rows]
         out["mel"] = mel
-        out["wave"] = g(mel.squeeze(1).permute(0, 2, 1))           # ddpm.py:932-935
+        out["wave"] = wave
     _save(name, out)
 
 
@@ -163,6 +167,7 @@ def main():
     R = ref_loader.load()
     full, tiny, tinyf = arch.model_config("audioldm2-full"), arch.tiny_config(), arch.tiny_config(film=True)
     tinyl, tiny48 = arch.tiny_config(variant="large"), arch.tiny_config(variant="48k")
+    m48, large = arch.model_config("audioldm_48k"), arch.model_config("audioldm2-full-large-1150k")
     jobs = {
         "unet_tiny_large": lambda: gen_unet(R, "unet_tiny_large", tinyl, 2, t5_len=5),
         "unet_tiny_48k": lambda: gen_unet(R, "unet_tiny_48k", tiny48, 2),
@@ -181,6 +186,15 @@ def main():
         "vocoder_full": lambda: gen_vocoder(R, "vocoder_full", full, 1, 1024),
         "ddim_full_10": lambda: gen_ddim(R, "ddim_full_10", full, 1, 10, with_audio=True),
         "ddim_full_200": lambda: gen_ddim(R, "ddim_full_200", full, 1, 200, with_audio=True),
+        # round 2: the benchmark shape (B = 8), the other BASELINE configs at full size, a full-size masked run
+        "unet_full_b8": lambda: gen_unet(R, "unet_full_b8", full, 8),
+        "ddim_full_10_b8": lambda: gen_ddim(R, "ddim_full_10_b8", full, 8, 10, with_audio=True, audio_rows=[0, 7]),
+        "ddim_full_10_masked": lambda: gen_ddim(R, "ddim_full_10_masked", full, 1, 10, masked=True, with_audio=True),
+        "unet_48k_full": lambda: gen_unet(R, "unet_48k_full", m48, 1),
+        "vae_48k_full": lambda: gen_vae(R, "vae_48k_full", m48, 1),
+        "vocoder_48k_full": lambda: gen_vocoder(R, "vocoder_48k_full", m48, 1, 1024),
+        "unet_large_full": lambda: gen_unet(R, "unet_large_full", large, 1),
+        "stft_48k": lambda: gen_stft(R, "stft_48k", 2048, 480, 256, 48000, 20, 24000, 491520),
     }
     for k, fn in jobs.items():
         if a.only and k != a.only:

@@ -2,9 +2,13 @@
 (a) the committed golden fixtures = outputs of the unmodified reference modules, and
 (b) the CPU oracle on the same seeded inputs.
 
-Tolerances: single network evaluation 1e-4 relative L2 (measured ~1e-5: operand planes carry
-2^-17 relative error, accumulation is fp32); end-to-end waveform after 10 / 200 DDIM steps 1e-3
-relative L2 -- the tolerance BASELINE.json's north_star states."""
+Tolerances (the precision budget is DESIGN.md section 3):
+* first-stage networks (VAE, HiFi-GAN: two-plane fp16 operands, 2^-22): 1e-4 relative L2 per evaluation (measured ~1e-6);
+* one UNet evaluation: the token-side operands (LayerNorm outputs, Q, K, V, softmax probabilities, GEGLU outputs) are single
+  fp16 planes (2^-12), the convolutions two planes: 1e-3 at full size (measured 4e-4), 3e-3 on the 32-channel toy topologies
+  (fewer channels to average the rounding over; measured 0.5-1.5e-3);
+* end-to-end waveform after 10 / 200 DDIM steps at full size: 1e-3 relative L2 -- the tolerance BASELINE.json's north_star
+  states (measured ~3e-4 / ~1e-4; the reference's own TF32 CUDA path is at 9e-4 against its fp32 path, bench.py)."""
 import numpy as np
 import pytest
 import torch
@@ -16,7 +20,15 @@ from tests.golden import cases
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 NET_TOL = 1e-4
+UNET_TOL = 1e-3
+TINY_UNET_TOL = 3e-3
+TINY_WAVE_TOL = 5e-3
 WAVE_TOL = 1e-3
+
+
+def _check(name, err, tol):
+    print(f"{name}: rel L2 {err:.2e} (tol {tol:.0e})")
+    assert err < tol, f"{name}: {err:.3e} >= {tol:.0e}"
 
 
 def _to(c, dev):
@@ -44,11 +56,12 @@ def test_unet_tiny(impl, tiny_tc):
     eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
     e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
     assert torch.isfinite(e_c).all()
-    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL, impl
-    assert rel_l2(e_c, g["eps_cond"]) < NET_TOL, impl
+    _check(f"unet_tiny/{impl}/uncond", rel_l2(e_u, g["eps_uncond"]), TINY_UNET_TOL)
+    _check(f"unet_tiny/{impl}/cond", rel_l2(e_c, g["eps_cond"]), TINY_UNET_TOL)
     # graph replay gives the same answer as the eager run
+    e_c1 = e_c.clone()
     e_u2, e_c2 = eng.apply_model_pair(x.to(DEV), int(t[0]))
-    assert rel_l2(e_c2, g["eps_cond"]) < NET_TOL
+    assert torch.equal(e_c2, e_c1)
 
 
 def test_unet_tiny_film():
@@ -58,7 +71,7 @@ def test_unet_tiny_film():
     x, t, cond, unc = cases.unet_inputs(cfg, 2)
     eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
     e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
-    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL and rel_l2(e_c, g["eps_cond"]) < NET_TOL
+    _check("unet_tiny_film", max(rel_l2(e_u, g["eps_uncond"]), rel_l2(e_c, g["eps_cond"])), TINY_UNET_TOL)
 
 
 def test_unet_tiny_large_topology():
@@ -68,7 +81,7 @@ def test_unet_tiny_large_topology():
     x, t, cond, unc = cases.unet_inputs(cfg, 2, t5_len=5)
     eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
     e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
-    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL and rel_l2(e_c, g["eps_cond"]) < NET_TOL
+    _check("unet_tiny_large", max(rel_l2(e_u, g["eps_uncond"]), rel_l2(e_c, g["eps_cond"])), TINY_UNET_TOL)
 
 
 def test_tiny_48k_topology():
@@ -80,7 +93,7 @@ def test_tiny_48k_topology():
     x, t, cond, unc = cases.unet_inputs(cfg, 2)
     eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
     e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
-    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL and rel_l2(e_c, g["eps_cond"]) < NET_TOL
+    _check("unet_tiny_48k", max(rel_l2(e_u, g["eps_uncond"]), rel_l2(e_c, g["eps_cond"])), TINY_UNET_TOL)
     gv = cases.load("vae_tiny_48k")
     assert rel_l2(eng.decode_first_stage(cases.latent(cfg, 2, seed=5).to(DEV)), gv["mel"]) < NET_TOL
     mom = eng.encode_first_stage_moments(cases.mel_input(cfg, 2).to(DEV))
@@ -123,7 +136,7 @@ def test_ddim_tiny_vs_reference(masked, tiny_tc):
     nf = lambda i, kind: (qn[i] if kind == "q" else noises[i]).to(DEV)
     z = tiny_tc.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=5, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf,
                                 mask=mask, x0=x0)
-    assert rel_l2(z, g["latent"]) < 2e-4
+    _check(f"ddim_tiny masked={masked}", rel_l2(z, g["latent"]), TINY_WAVE_TOL)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -140,8 +153,8 @@ def test_unet_full_vs_reference(full):
     x, t, cond, unc = cases.unet_inputs(cfg, 1)
     full.set_conditioning(_to(cond, DEV), _to(unc, DEV))
     e_u, e_c = full.apply_model_pair(x.to(DEV), int(t[0]))
-    assert rel_l2(e_u, g["eps_uncond"]) < NET_TOL
-    assert rel_l2(e_c, g["eps_cond"]) < NET_TOL
+    _check("unet_full/uncond", rel_l2(e_u, g["eps_uncond"]), UNET_TOL)
+    _check("unet_full/cond", rel_l2(e_c, g["eps_cond"]), UNET_TOL)
 
 
 def test_vae_vocoder_full_vs_reference(full):
@@ -210,7 +223,7 @@ def test_pipeline_text_to_audio_tiny():
         z = OF.ddim_sample(synth.unet_state_dict(cfg["unet"]), cfg["unet"], x_T, noises, cond, unc, S, 1.0, 3.5,
                            OF.ddpm_tables(cfg["linear_start"], cfg["linear_end"], cfg["timesteps"]))
         ref = _oracle_wave(cfg, z)
-    assert rel_l2(torch.from_numpy(wav), ref) < WAVE_TOL
+    _check("pipeline text_to_audio tiny", rel_l2(torch.from_numpy(wav), ref), TINY_WAVE_TOL)
     # n_candidate_gen_per_text > 1: candidates of prompt i are rows i + k*B; a ranker picks per prompt (ddpm.py:1554-1564)
     picked = {}
 
@@ -237,7 +250,7 @@ def test_pipeline_super_resolution_and_inpainting_tiny():
     cfg = arch.tiny_config()
     vc = cfg["vocoder"]
     ld = A.build_model(config=cfg, t5_len=5)
-    B, S, seed = 2, 3, 11
+    B, S, seed = 2, 4, 11
     wav_in = cases.wav_input(5000).numpy()[0]                      # longer than the segment: cropped (tools.py:8-18)
     dur = 1.28                                                     # 128 mel frames at hop 40 / 4 kHz -> latent T = 32
     out = A.super_resolution_and_inpainting(ld, "x", seed=seed, ddim_steps=S, duration=dur, batchsize=B, n_candidate_gen_per_text=1,
@@ -262,14 +275,14 @@ def test_pipeline_super_resolution_and_inpainting_tiny():
                            OF.ddpm_tables(cfg["linear_start"], cfg["linear_end"], cfg["timesteps"]), mask=mask, x0=x0, q_noises=qn)
         ref = _oracle_wave(cfg, z)
     assert out.shape == tuple(ref.shape)
-    assert rel_l2(torch.from_numpy(out), ref) < WAVE_TOL
+    _check("pipeline sr_inpainting tiny", rel_l2(torch.from_numpy(out), ref), TINY_WAVE_TOL)
 
 
 def test_rank_shards_reproduce_single_process_batch(tiny_tc):
     """two ranks (B = 1 each, full-batch noise drawn and sliced) == one process with B = 2."""
     from audioldm2_b200 import parallel
     cfg = arch.tiny_config()
-    S = 3
+    S = 4
     cond, unc = synth.conditioning(cfg, 2, seed=77, t5_len=5)
     sn = parallel.ShardedNoise(2, 0, 2, cfg["latent"], DEV, seed=42)
     z_full = tiny_tc.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=S, guidance=3.5, eta=1.0, x_T=sn.x_T(), noise_fn=sn).clone()
@@ -278,4 +291,103 @@ def test_rank_shards_reproduce_single_process_batch(tiny_tc):
         sr_ = parallel.ShardedNoise(2, r, r + 1, cfg["latent"], DEV, seed=42)
         c, u = parallel.shard_rows(cond, r, r + 1), parallel.shard_rows(unc, r, r + 1)
         z = e1.generate_latent(_to(c, DEV), _to(u, DEV), ddim_steps=S, guidance=3.5, eta=1.0, x_T=sr_.x_T(), noise_fn=sr_)
-        assert rel_l2(z, z_full[r:r + 1]) < 2e-5, r
+        assert rel_l2(z, z_full[r:r + 1]) < 1e-3, r      # same noise, same weights; fp16 roundings may flip with the batch-dependent split-K order
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the benchmark shape (batch 8) and the other BASELINE configs at FULL size, against reference fixtures
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_b8():
+    return _engine(arch.model_config("audioldm2-full"), 8, 32)
+
+
+def test_unet_full_batch8_vs_reference(full_b8):
+    """The benchmark's GEMM shapes: 2 * 8 rows, M = 65536 / 16384 / 4096 / 1024 (tile counts, split-K and N-tile choices
+    differ from the B = 1 plan)."""
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load("unet_full_b8")
+    x, t, cond, unc = cases.unet_inputs(cfg, 8)
+    full_b8.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = full_b8.apply_model_pair(x.to(DEV), int(t[0]))
+    _check("unet_full_b8/uncond", rel_l2(e_u, g["eps_uncond"]), UNET_TOL)
+    _check("unet_full_b8/cond", rel_l2(e_c, g["eps_cond"]), UNET_TOL)
+    for b in range(8):          # per sample, not only on average
+        assert rel_l2(e_c[b], g["eps_cond"][b]) < 2 * UNET_TOL, b
+
+
+def test_end_to_end_batch8_vs_reference(full_b8):
+    """Batch 8, 10 DDIM steps, decode + vocoder: latent of all rows, mel / waveform of the stored rows (0 and 7)."""
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load("ddim_full_10_b8")
+    _, _, cond, unc = cases.unet_inputs(cfg, 8)
+    x_T, noises, _ = cases.sampler_noise(cfg, 8, 10)
+    nf = lambda i, kind: noises[i].to(DEV)
+    z = full_b8.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=10, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf)
+    _check("b8 latent", rel_l2(z, g["latent"]), WAVE_TOL)
+    rows = g["audio_rows"].tolist()
+    mel = full_b8.decode_first_stage(z)
+    _check("b8 mel", rel_l2(mel[rows], g["mel"]), WAVE_TOL)
+    wave = full_b8.mel_spectrogram_to_waveform(mel)
+    _check("b8 waveform", rel_l2(wave[rows], g["wave"]), WAVE_TOL)
+
+
+def test_masked_full_size_vs_reference(full):
+    """generate_batch_masked's sampler at full size (ddim.py:226-231): mask over time rows [0.4, 0.6), 10 steps."""
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load("ddim_full_10_masked")
+    _, _, cond, unc = cases.unet_inputs(cfg, 1)
+    x_T, noises, qn = cases.sampler_noise(cfg, 1, 10, masked=True)
+    mask, x0 = cases.inpaint_mask(cfg, 1)
+    nf = lambda i, kind: (qn[i] if kind == "q" else noises[i]).to(DEV)
+    z = full.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=10, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf,
+                             mask=mask.to(DEV), x0=x0.to(DEV))
+    _check("masked latent", rel_l2(z, g["latent"]), WAVE_TOL)
+    wave = full.mel_spectrogram_to_waveform(full.decode_first_stage(z))
+    _check("masked waveform", rel_l2(wave, g["wave"]), WAVE_TOL)
+
+
+def test_vae_encoder_full_vs_reference(full):
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load("vae_full")
+    mom = full.encode_first_stage_moments(cases.mel_input(cfg, 1).to(DEV))
+    _check("vae_full moments", rel_l2(mom.permute(0, 3, 1, 2), g["moments"]), NET_TOL)
+
+
+def test_large_unet_full_size_vs_reference():
+    """audioldm2-full-large-1150k (utils.py:118-120): 4 STs per site, transformer_depth 2, 2.87 GB of weights."""
+    cfg = arch.model_config("audioldm2-full-large-1150k")
+    eng = _engine(cfg, 1, 32)
+    g = cases.load("unet_large_full")
+    x, t, cond, unc = cases.unet_inputs(cfg, 1)
+    eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
+    _check("unet_large_full/uncond", rel_l2(e_u, g["eps_uncond"]), UNET_TOL)
+    _check("unet_large_full/cond", rel_l2(e_c, g["eps_cond"]), UNET_TOL)
+
+
+def test_48k_full_size_vs_reference():
+    """audioldm_48k (utils.py:413-561): FiLM UNet on the 16 x 128 x 32 latent, 4-level VAE (1024-channel mid attention over
+    4096 tokens, 1024 x 256 mel), HiFi-GAN with four MRF kernels (k up to 15) -> 491,536 samples."""
+    from audioldm2_b200 import engine
+    cfg = arch.model_config("audioldm_48k")
+    eng = _engine(cfg, 1, 32, with_encoder=True)
+    g = cases.load("unet_48k_full")
+    x, t, cond, unc = cases.unet_inputs(cfg, 1)
+    eng.set_conditioning(_to(cond, DEV), _to(unc, DEV))
+    e_u, e_c = eng.apply_model_pair(x.to(DEV), int(t[0]))
+    _check("unet_48k_full/uncond", rel_l2(e_u, g["eps_uncond"]), UNET_TOL)
+    _check("unet_48k_full/cond", rel_l2(e_c, g["eps_cond"]), UNET_TOL)
+    gv = cases.load("vae_48k_full")
+    _check("vae_48k_full mel", rel_l2(eng.decode_first_stage(cases.latent(cfg, 1, seed=5).to(DEV)), gv["mel"]), NET_TOL)
+    mom = eng.encode_first_stage_moments(cases.mel_input(cfg, 1).to(DEV))
+    _check("vae_48k_full moments", rel_l2(mom.permute(0, 3, 1, 2), gv["moments"]), NET_TOL)
+    gw = cases.load("vocoder_48k_full")
+    melin = cases.vocoder_input(cfg, 1, 1024).permute(0, 2, 1).contiguous()[:, None]
+    w = eng.mel_spectrogram_to_waveform(melin.to(DEV))
+    assert w.shape == (1, 1, 491536)
+    _check("vocoder_48k_full wave", rel_l2(w, gw["wave"]), NET_TOL)
+    gs = cases.load("stft_48k")                                     # reference TacotronSTFT(2048, 480, 2048, 256, 48000, 20, 24000)
+    from audioldm2_b200 import frontend
+    got = engine.stft_mel(cases.wav_input(491520).to(DEV).contiguous(), 2048, 480, frontend.mel_basis_for(cfg).to(DEV))
+    _check("stft_48k logmel", rel_l2(got[0].t(), gs["logmel"][0]), NET_TOL)

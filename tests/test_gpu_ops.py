@@ -1,9 +1,11 @@
 """GPU parity tests of the individual kernels, called through the C-ABI (ctypes) and compared with
 the CPU oracle / op-table emulator on the same seeded inputs.
 
-Tolerances (written per test): elementwise kernels 1e-6; kernels behind bf16 hi/lo operand planes
-2e-5 relative L2 (operand representation error 2^-17); the emulator applies the same operand
-splitting, so GEMM-vs-emulator comparisons are at accumulate-order noise (<= 1e-5)."""
+Tolerances (written per test): elementwise kernels 1e-6; kernels behind fp16 hi/lo operand planes 2e-5 relative L2
+(the emulator applies the same operand splitting, so GEMM-vs-emulator comparisons are at accumulate-order noise,
+<= 1e-5; planes themselves carry 2^-22); single-plane outputs are compared after the same fp16 rounding (one-ulp flips
+of a 2^-12 rounding: 3e-4 bound); the attention kernel rounds its probabilities to fp16 relative to the RUNNING row
+maximum while the emulator rounds relative to the final one, so that comparison is bounded by 5e-4."""
 import ctypes as C
 import math
 
@@ -41,9 +43,10 @@ def read_gpu_f32(prog, ref: Ref, n: int):
 
 def read_gpu_planes(prog, p: Planes):
     n = p.rows * p.Cp
-    hi = prog.ws[p.hi.off:p.hi.off + 2 * n].view(torch.bfloat16).float().cpu()
-    lo = prog.ws[p.lo.off:p.lo.off + 2 * n].view(torch.bfloat16).float().cpu()
-    return (hi + lo).reshape(p.rows, p.Cp)
+    x = prog.ws[p.hi.off:p.hi.off + 2 * n].view(torch.float16).float().cpu()
+    if p.lo is not None:
+        x = x + prog.ws[p.lo.off:p.lo.off + 2 * n].view(torch.float16).float().cpu()
+    return x.reshape(p.rows, p.Cp)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -94,8 +97,9 @@ def test_groupnorm_fast_path():
         assert rel_l2(read_gpu_planes(prog, o), em.read_planes(o.hi, o.lo, o.rows, o.Cp)) < 2e-5
 
 
+@pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("mode", ["copy", "silu", "lrelu", "gn", "gn_silu", "ln", "nchw", "cat", "pad"])
-def test_prep_modes(mode):
+def test_prep_modes(mode, planes):
     g = torch.Generator().manual_seed(2)
     P = Planner(keep_plain=True)
     B, HW = 3, 50
@@ -110,22 +114,24 @@ def test_prep_modes(mode):
     m = dict(copy=_lib.PREP_COPY, silu=_lib.PREP_SILU, lrelu=_lib.PREP_LRELU, gn=_lib.PREP_GN, gn_silu=_lib.PREP_GN_SILU,
              ln=_lib.PREP_LN, nchw=_lib.PREP_COPY, cat=_lib.PREP_GN_SILU, pad=_lib.PREP_COPY)[mode]
     out = P.prep(m, src, src2 if mode == "cat" else None, gam, bet, eps=1e-5 if mode != "gn" else 1e-6, slope=0.1,
-                 B=B, HW=HW, src_nchw=(mode == "nchw"))
+                 B=B, HW=HW, src_nchw=(mode == "nchw"), n=planes)
+    assert (out.lo is None) == (planes == 1)
     pl = P.finish(dict(a=("f32", src.ref, (src.rows, src.C)), b=("f32", src2.ref, (src2.rows, src2.C))))
     em, prog = run_both(pl, dict(a=torch.randn(src.rows, src.C, generator=g) * 2 + 0.3,
                                  b=torch.randn(src2.rows, src2.C, generator=g)))
     want = em.read_planes(out.hi, out.lo, out.rows, out.Cp)
     got = read_gpu_planes(prog, out)
     assert torch.isfinite(got).all()
-    assert rel_l2(got, want) < 2e-5, mode
+    assert rel_l2(got, want) < (2e-5 if planes == 2 else 3e-4), mode
 
 
 def _gemm_case(P: Planner, g, *, B, H, W, Cin, N, taps, OH=None, OW=None, sy=1, sx=1, up=0, bmod=0, act=_lib.ACT_NONE,
-               res=False, rowvec=False, alpha=1.0, accumulate=False, out_kind="f32", geglu=False, bias=True, dual=False):
+               res=False, rowvec=False, alpha=1.0, accumulate=False, out_kind="f32", geglu=False, bias=True, dual=False,
+               a_planes=2, out_planes_n=2):
     Hs, Ws = H >> up, W >> up
     Bsrc = bmod if bmod else B
     src = F32(P.raw(Bsrc * Hs * Ws * Cin * 4), Bsrc * Hs * Ws, Cin)
-    a = P.prep(_lib.PREP_COPY, src)
+    a = P.prep(_lib.PREP_COPY, src, n=a_planes)
     cp = a.Cp
     wm = torch.zeros(N, len(taps), cp)
     wm[:, :, :Cin] = torch.randn(N, len(taps), Cin, generator=g) / math.sqrt(len(taps) * Cin)
@@ -146,13 +152,13 @@ def _gemm_case(P: Planner, g, *, B, H, W, Cin, N, taps, OH=None, OW=None, sy=1, 
         o = P.f32(M, n_out); kw["out"] = o
         ios["out"] = ("f32", o.ref, (M, n_out)); ins["out"] = torch.randn(M, n_out, generator=g)   # for accumulate
         if dual:
-            dp = P.planes(M, n_out); kw["also_planes"] = dp
+            dp = P.planes(M, n_out, out_planes_n); kw["also_planes"] = dp
             P.gemm(a, w, **kw)
             return ios, ins, ("dual", (o, dp))
         P.gemm(a, w, **kw)
         return ios, ins, ("f32", o)
     if out_kind == "planes":
-        o = P.planes(M, n_out); kw["out_planes"] = o
+        o = P.planes(M, n_out, out_planes_n); kw["out_planes"] = o
         P.gemm(a, w, **kw)
         return ios, ins, ("planes", o)
     o = P.raw(B * N * OHv * OWv * 4)
@@ -176,29 +182,32 @@ GEMM_CASES = {
     "deepK_splitk": dict(B=2, H=8, W=2, Cin=640, N=640, taps=plan.TAPS_3x3, res=True, rowvec=True),
     "nobias": dict(B=1, H=130, W=1, Cin=96, N=288, taps=((0, 0),), bias=False),
     "dual_out": dict(B=1, H=300, W=1, Cin=128, N=256, taps=((0, 0),), res=True, dual=True),
+    # single-plane activations (two UMMAs per K step, 4-stage ring) and single-plane outputs: the token side of the UNet
+    "a1_linear_big": dict(B=1, H=1000, W=1, Cin=640, N=384, taps=((0, 0),), res=True, a_planes=1),
+    "a1_geglu_p1": dict(B=1, H=200, W=1, Cin=256, N=512, taps=((0, 0),), geglu=True, act=_lib.ACT_GEGLU, out_kind="planes",
+                        a_planes=1, out_planes_n=1),
+    "a1_planes_p1": dict(B=1, H=260, W=1, Cin=128, N=256, taps=((0, 0),), out_kind="planes", a_planes=1, out_planes_n=1),
+    "a1_dual_p2": dict(B=1, H=300, W=1, Cin=1024, N=256, taps=((0, 0),), res=True, dual=True, a_planes=1),
+    "a1_conv3x3": dict(B=2, H=20, W=6, Cin=24, N=128, taps=plan.TAPS_3x3, rowvec=True, res=True, a_planes=1),
+    "a1_deepK_splitk": dict(B=2, H=8, W=2, Cin=640, N=640, taps=plan.TAPS_3x3, res=True, a_planes=1),
 }
-if os.environ.get("ALDM_BN256") == "1":      # extra shapes for the experimental 128 x 256 tile (scripts/gpu_experiments.sh)
-    GEMM_CASES.update({
-        "bn256_linear_res": dict(B=1, H=700, W=1, Cin=256, N=512, taps=((0, 0),), res=True),
-        "bn256_conv_rowvec": dict(B=2, H=24, W=8, Cin=64, N=256, taps=plan.TAPS_3x3, rowvec=True, res=True),
-        "bn256_planes": dict(B=1, H=260, W=1, Cin=128, N=256, taps=((0, 0),), out_kind="planes"),
-        "bn256_splitk": dict(B=2, H=8, W=2, Cin=256, N=256, taps=plan.TAPS_3x3, res=True),
-    })
 
-
-@pytest.mark.parametrize("impl", ["simt", "tc", "tc1"])
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("case", sorted(GEMM_CASES))
 def test_gemm_vs_emulator(case, impl):
     g = torch.Generator().manual_seed(sum(map(ord, case)))
     P = Planner(impl=impl, keep_plain=True)
     ios, ins, (kind, o) = _gemm_case(P, g, **GEMM_CASES[case])
     pl = P.finish(ios)
-    if case == "deepK_splitk" and impl != "simt":
+    if case.endswith("deepK_splitk") and impl != "simt":
         assert pl.ops[-1]["splitk"] > 1
+    if case.startswith("a1_"):
+        assert pl.ops[-1]["a_lo"] is None
     em, prog = run_both(pl, ins)
+    ptol = 3e-4 if GEMM_CASES[case].get("out_planes_n", 2) == 1 else 2e-5      # single plane: one-ulp flips of an 11-bit rounding
     if kind == "dual":
         o, dp = o
-        assert rel_l2(read_gpu_planes(prog, dp), em.read_planes(dp.hi, dp.lo, dp.rows, dp.Cp)) < 2e-5
+        assert rel_l2(read_gpu_planes(prog, dp), em.read_planes(dp.hi, dp.lo, dp.rows, dp.Cp)) < ptol
         kind = "f32"
     if kind == "f32":
         want, got = em.f32(o.ref, o.rows * o.C).clone(), read_gpu_f32(prog, o.ref, o.rows * o.C)
@@ -208,7 +217,7 @@ def test_gemm_vs_emulator(case, impl):
         want, got = em.f32(o[0], o[1]).clone(), read_gpu_f32(prog, o[0], o[1])
     assert torch.isfinite(got).all(), f"{case}/{impl}: non-finite output"
     err = rel_l2(got, want)
-    assert err < 2e-5, f"{case}/{impl}: rel L2 {err:.3e}"
+    assert err < (ptol if kind == "planes" else 2e-5), f"{case}/{impl}: rel L2 {err:.3e}"
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
@@ -227,16 +236,16 @@ def test_attention(case, impl):
     selfattn = case.startswith("self")
     ldq = 2 * Cc if selfattn else Cc
     qf = F32(P.raw(B * Nq * ldq * 4), B * Nq, ldq)
-    qp = P.prep(_lib.PREP_COPY, qf)
+    qp = P.prep(_lib.PREP_COPY, qf, n=1)
     ios = dict(q=("f32", qf.ref, (B * Nq, ldq)))
     ins = dict(q=torch.randn(B * Nq, ldq, generator=g))
-    vt = P.vt(Bkv, Cc, Nk)
+    vt = P.vt(Bkv, Cc, Nk, 1)
     mk = None
     if selfattn:
         kp, kcol = qp, Cc
     else:
         kf = F32(P.raw(Bkv * Nk * Cc * 4), Bkv * Nk, Cc)
-        kp, kcol = P.prep(_lib.PREP_COPY, kf), 0
+        kp, kcol = P.prep(_lib.PREP_COPY, kf, n=1), 0
         ios["k"] = ("f32", kf.ref, (Bkv * Nk, Cc)); ins["k"] = torch.randn(Bkv * Nk, Cc, generator=g)
         if case != "ragged":
             mk = P.raw(Bkv * Nk * 4)
@@ -244,49 +253,53 @@ def test_attention(case, impl):
             if case == "cross_allmasked":
                 m[1] = 0          # fully-masked row -> uniform weights (SURVEY.md 8a' item 5)
             ios["mask"] = ("f32", mk, (Bkv, Nk)); ins["mask"] = m
-    ao = P.planes(B * Nq, Cc)
+    ao = P.planes(B * Nq, Cc, 1)
     P.attn(qp, 0, kp, kcol, vt, ao, B=B, heads=heads, Nq=Nq, Nk=Nk, mask=mk, scale=32 ** -0.5,
            kv_bmod=1 if case.endswith("bmod") else 0)
     pl = P.finish(ios)
     # V^T planes are written directly (in the network they come from an ALDM_OUT_QKV GEMM)
     v = torch.randn(Bkv, Cc, vt.ld_t, generator=g)
     v[:, :, Nk:] = 0
-    vh = v.to(torch.bfloat16); vl = (v - vh.float()).to(torch.bfloat16)
+    vh = v.to(torch.float16)
     em = Emulator(pl)
     prog = engine.DeviceProgram(pl, torch.device(DEV), dict(all=(0, len(pl.ops))))
     n = Bkv * Cc * vt.ld_t
-    em.bf16(vt.hi, n)[:] = vh.reshape(-1); em.bf16(vt.lo, n)[:] = vl.reshape(-1)
-    prog.ws[vt.hi.off:vt.hi.off + 2 * n].view(torch.bfloat16).copy_(vh.reshape(-1))
-    prog.ws[vt.lo.off:vt.lo.off + 2 * n].view(torch.bfloat16).copy_(vl.reshape(-1))
+    em.f16(vt.hi, n)[:] = vh.reshape(-1)
+    prog.ws[vt.hi.off:vt.hi.off + 2 * n].view(torch.float16).copy_(vh.reshape(-1))
     for name, val in ins.items():
         em.write_io(name, val); prog.view(name).copy_(val.to(DEV))
     em.run(); prog.run("all"); torch.cuda.synchronize()
     got, want = read_gpu_planes(prog, ao), em.read_planes(ao.hi, ao.lo, ao.rows, ao.Cp)
     assert torch.isfinite(got).all()
     err = rel_l2(got, want)
-    assert err < 2e-5, f"{case}/{impl}: {err:.3e}"
+    assert err < 5e-4, f"{case}/{impl}: {err:.3e}"
 
 
+@pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("impl", ["simt", "tc"])
-def test_gemm_qkv_output(impl):
+def test_gemm_qkv_output(impl, planes):
     """ALDM_OUT_QKV: Q|K columns as planes, V columns as transposed planes (keys contiguous, pad zeroed)."""
     g = torch.Generator().manual_seed(11)
     P = Planner(impl=impl, keep_plain=True)
     Bt, HW, Cc = 3, 37, 64
     rows = Bt * HW
     src = F32(P.raw(rows * Cc * 4), rows, Cc)
-    a = P.prep(_lib.PREP_COPY, src)
+    a = P.prep(_lib.PREP_COPY, src, n=planes)
     wm = torch.randn(3 * Cc, Cc, generator=g) / 8
     w = P.wmat(wm, None, 1, Cc, bn=P.bn_for_split(3 * Cc, 2 * Cc))
-    qk = P.planes(rows, 2 * Cc)
-    vt = P.vt(Bt, Cc, HW)
+    qk = P.planes(rows, 2 * Cc, planes)
+    vt = P.vt(Bt, Cc, HW, planes)
     P.gemm(a, w, B=1, H=rows, qkv=(qk, vt, 2 * Cc, HW))
     em, prog = run_both(P.finish(dict(src=("f32", src.ref, (rows, Cc)))), dict(src=torch.randn(rows, Cc, generator=g)))
-    assert rel_l2(read_gpu_planes(prog, qk), em.read_planes(qk.hi, qk.lo, rows, qk.Cp)) < 2e-5
+    tol = 2e-5 if planes == 2 else 3e-4
+    assert rel_l2(read_gpu_planes(prog, qk), em.read_planes(qk.hi, qk.lo, rows, qk.Cp)) < tol
     n = Bt * Cc * vt.ld_t
-    gv = (prog.ws[vt.hi.off:vt.hi.off + 2 * n].view(torch.bfloat16).float() + prog.ws[vt.lo.off:vt.lo.off + 2 * n].view(torch.bfloat16).float()).cpu()
-    ev = em.bf16(vt.hi, n).float() + em.bf16(vt.lo, n).float()
-    assert torch.isfinite(gv).all() and rel_l2(gv, ev) < 2e-5
+    gv = prog.ws[vt.hi.off:vt.hi.off + 2 * n].view(torch.float16).float().cpu()
+    ev = em.f16(vt.hi, n).float()
+    if planes == 2:
+        gv = gv + prog.ws[vt.lo.off:vt.lo.off + 2 * n].view(torch.float16).float().cpu()
+        ev = ev + em.f16(vt.lo, n).float()
+    assert torch.isfinite(gv).all() and rel_l2(gv, ev) < tol
     assert float(gv.reshape(Bt, Cc, vt.ld_t)[:, :, HW:].abs().max()) == 0.0
 
 

@@ -1,9 +1,10 @@
 """CPU checks of the host side: planner + weight packing, executed by the op-table emulator and
 compared with the reference-module fixtures (tests/golden).  These validate everything the GPU
 will be told to do -- graph wiring, K ordering, GEGLU row permutation, polyphase transposed
-convolutions, buffer reuse -- without a GPU.  Tolerance: the emulator keeps activations as
-bf16 hi+lo pairs like the kernels do (relative 2^-17 per operand), so agreement with the fp32
-reference is ~1e-5; the bound asserted is 2e-4 relative L2."""
+convolutions, buffer reuse -- without a GPU.  Tolerance: the emulator keeps operands as fp16 planes like the
+kernels do -- hi + lo (2^-22) for weights and convolution inputs, a single plane (2^-12) for the
+token-side activations of the UNet -- so first-stage networks agree with the fp32 reference to ~1e-6
+(bound 2e-4) and a UNet evaluation to a few 1e-4 (bound UNET_TOL)."""
 import pytest
 import torch
 
@@ -13,6 +14,8 @@ from tests.emulator import Emulator
 from tests.golden import cases
 
 TOL = 2e-4
+UNET_TOL = 3e-3          # 32-channel toy topologies with single-plane token operands: measured 0.5-1.5e-3 per evaluation
+                         # (full size: 4e-4, tests/test_gpu_nets.py; the end-to-end budget is 1e-3 on the waveform)
 
 
 def test_pack_roundtrip_and_swizzle():
@@ -22,50 +25,13 @@ def test_pack_roundtrip_and_swizzle():
         packed, plain, Npad, Kpad = packing.pack_tiles(w, bn)
         assert packed.numel() == Npad * Kpad * 4
         back = packing.unpack_tiles(packed, N, K, bn)
-        assert rel_l2(back, w) < 2e-5
+        assert rel_l2(back, w) < 1e-6
         # address formula used by the kernels: row r, logical chunk j -> r*128 + ((j ^ (r&7))<<4)
-        hi = packed.view(torch.bfloat16).reshape(Npad // bn, Kpad // 64, 2, bn * 64)[0, 0, 0]
+        hi = packed.view(torch.float16).reshape(Npad // bn, Kpad // 64, 2, bn * 64)[0, 0, 0]
         r, j = min(5, N - 1), 3
         off = (r * 128 + ((j ^ (r & 7)) << 4)) // 2
-        want = plain[r, j * 8:(j + 1) * 8].to(torch.bfloat16)
+        want = plain[r, j * 8:(j + 1) * 8].to(torch.float16)
         assert torch.equal(hi[off:off + 8], want)
-
-
-def test_bn256_tiles_plan(monkeypatch):
-    """EXPERIMENTAL 128 x 256 tiles (ALDM_BN256=1): packing, GEGLU row order and QKV split stay consistent with the
-    emulator's reading of the packed image (the kernel side is validated on hardware by scripts/gpu_experiments.sh)."""
-    import math
-    from audioldm2_b200 import _lib
-    from audioldm2_b200.plan import F32, Planner
-    monkeypatch.setenv("ALDM_BN256", "1")
-    g = torch.Generator().manual_seed(3)
-    M, K, N = 200, 96, 512
-    x = torch.randn(M, K, generator=g)
-    for geglu in (False, True):
-        P = Planner()
-        assert P.bn256
-        src = F32(P.raw(M * K * 4), M, K)
-        a = P.prep(_lib.PREP_COPY, src)
-        wm = torch.randn(N, K, generator=g) / math.sqrt(K)
-        bias = torch.randn(N, generator=g)
-        w = P.wmat(wm, bias, 1, K, geglu=geglu)
-        assert w.bn == 256
-        if geglu:
-            out = P.planes(M, N // 2)
-            P.gemm(a, w, B=1, H=M, out_planes=out, act=_lib.ACT_GEGLU)
-            y = x @ wm.t() + bias
-            want = y[:, :N // 2] * torch.nn.functional.gelu(y[:, N // 2:])
-        else:
-            o = P.f32(M, N)
-            P.gemm(a, w, B=1, H=M, out=o)
-            want = x @ wm.t() + bias
-        pl = P.finish(dict(src=("f32", src.ref, (M, K))))
-        em = Emulator(pl)
-        em.write_io("src", x)
-        em.run()
-        got = em.read_planes(out.hi, out.lo, M, out.Cp) if geglu else em.f32(o.ref, M * N).reshape(M, N)
-        assert rel_l2(got, want) < 2e-5
-    assert Planner().bn_for_split(768, 512) == 256
 
 
 def test_geglu_row_order():
@@ -116,11 +82,12 @@ def _run_unet(cfg, B, t5_len, fixture, film=False):
     em.run(pl.marks["step_begin"], pl.marks["step_end"])
     eps = em.read_io("eps")
     g = cases.load(fixture)
-    assert rel_l2(eps[:B], g["eps_uncond"]) < TOL
-    assert rel_l2(eps[B:], g["eps_cond"]) < TOL
+    eu, ec = rel_l2(eps[:B], g["eps_uncond"]), rel_l2(eps[B:], g["eps_cond"])
+    print(f"{fixture}: eps rel L2 uncond {eu:.2e} cond {ec:.2e}")
+    assert eu < UNET_TOL and ec < UNET_TOL
     # second evaluation on the same workspace (buffer reuse must not depend on stale state)
     em.run(pl.marks["step_begin"], pl.marks["step_end"])
-    assert rel_l2(em.read_io("eps")[B:], g["eps_cond"]) < TOL
+    assert rel_l2(em.read_io("eps")[B:], g["eps_cond"]) < UNET_TOL
 
 
 def test_unet_tiny_plan():
