@@ -36,16 +36,20 @@ class ShardedNoise:
     order, ddim.py:191,351 / ddpm.py:431) from the same seed with the same generator and keeps rows [lo, hi) -- 131 KB per
     sample and draw, no communication.  Use as ``x_T=sn.x_T(), noise_fn=sn`` of ``generate_latent``."""
 
-    def __init__(self, global_batch: int, lo: int, hi: int, latent, device, seed: int = 42, generator=None):
+    def __init__(self, global_batch: int, lo: int, hi: int, latent, device, seed: int = 42, generator=None, rows=None):
+        """Rows [lo, hi) of the global batch, or an explicit index list ``rows`` (the candidates of prompt i sit at
+        rows i + k * batchsize, ddpm.py:1560-1562, so a rank that owns prompts [lo, hi) owns a strided row set)."""
         self.shape = (int(global_batch),) + tuple(int(v) for v in latent)
         self.lo, self.hi, self.device = lo, hi, torch.device(device)
+        self.rows = None if rows is None else torch.as_tensor(rows, dtype=torch.long, device=self.device)
         if generator is None:
             generator = torch.Generator(device=self.device)
             generator.manual_seed(int(seed))
         self.gen = generator
 
     def _draw(self) -> torch.Tensor:
-        return torch.randn(self.shape, device=self.device, generator=self.gen)[self.lo:self.hi].contiguous()
+        full = torch.randn(self.shape, device=self.device, generator=self.gen)
+        return (full[self.lo:self.hi] if self.rows is None else full[self.rows]).contiguous()
 
     def x_T(self) -> torch.Tensor:
         return self._draw()
@@ -65,6 +69,30 @@ def shard_rows(t, lo: int, hi: int):
     if isinstance(t, (list, tuple)):
         return [shard_rows(v, lo, hi) for v in t]
     return t
+
+
+def current_shard(n_items: int):
+    """(rank, world, lo, hi) of this process for ``n_items`` independent units, or None in a single-process run."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    r, w = dist.get_rank(), dist.get_world_size()
+    lo, hi = shard_range(n_items, r, w)
+    return r, w, lo, hi
+
+
+def all_gather_rows(local: torch.Tensor, n_items: int) -> torch.Tensor:
+    """Concatenate the ranks' row shards (shard_range order) into the full [n_items, ...] tensor on every rank: the one
+    collective at the END of a sharded generation; shards may differ by one row."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    w = dist.get_world_size()
+    sizes = [shard_range(n_items, r, w) for r in range(w)]
+    mx = max(b - a for a, b in sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(w)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([bufs[r][:b - a] for r, (a, b) in enumerate(sizes)], dim=0)
 
 
 def make_arena_bcast(device, src: int = 0):

@@ -22,7 +22,7 @@ from typing import Callable, Dict, Optional, Tuple
 import numpy as np
 import torch
 
-from . import arch, engine, frontend, model, synth
+from . import arch, engine, frontend, model, parallel, synth
 from .utils import seed_everything
 
 
@@ -131,6 +131,25 @@ class NativeAudioLDM2:
 
     def _generate(self, batch, ddim_steps, ddim_eta, x_T, n_gen, guidance, uncond, use_plms, tmask, fmask):
         assert x_T is None and not use_plms, "the native path implements the DDIM sampler (pipeline.py never asks for PLMS)"
+        shard = parallel.current_shard(len(batch["text"]))
+        if shard is not None:              # one process per GPU: this rank generates prompts [lo, hi) of the call
+            return self._generate_sharded(shard, batch, ddim_steps, ddim_eta, n_gen, guidance, uncond, tmask, fmask)
+        return self._generate_local(batch, ddim_steps, ddim_eta, n_gen, guidance, uncond, tmask, fmask, None)
+
+    def _generate_sharded(self, shard, batch, ddim_steps, ddim_eta, n_gen, guidance, uncond, tmask, fmask):
+        """Every rank runs the same call with the same seed; prompts are cut into contiguous shards, the noise of the
+        single-process latent batch (rows i + k * B) is drawn in full on every rank and sliced, and the selected waveforms are
+        all-gathered at the end.  Results equal the single-process call row for row."""
+        _, _, lo, hi = shard
+        B = len(batch["text"])
+        local = {k: (v[lo:hi] if (torch.is_tensor(v) or isinstance(v, list)) and len(v) == B else v) for k, v in batch.items()}
+        rows = [i + k * B for k in range(n_gen) for i in range(lo, hi)]
+        cond_l = parallel.shard_rows(self.cond_provider.cond(batch), lo, hi)       # conditioning of the whole call, this rank's rows
+        out = self._generate_local(local, ddim_steps, ddim_eta, n_gen, guidance, uncond, tmask, fmask, (B, rows), cond_l)
+        full = parallel.all_gather_rows(torch.from_numpy(out).to(self.device), B)
+        return self._egress(full)
+
+    def _generate_local(self, batch, ddim_steps, ddim_eta, n_gen, guidance, uncond, tmask, fmask, glob, cond_rows=None):
         masked = tmask is not None
         B = len(batch["text"])
         Bl = B * n_gen
@@ -139,7 +158,15 @@ class NativeAudioLDM2:
         # get_input -> encode_first_stage -> posterior.sample() (ddpm.py:845-846): a CPU torch.randn of the latent shape
         # (distributions.py:38).  Plain text_to_audio encodes an all-zero fbank only to read z.shape[0]; that encoder pass is
         # skipped here (345 GFLOP per prompt), the CPU draw is kept so every later CPU draw sees the reference's RNG state.
-        post_noise = torch.randn(B, C_, T, F_)
+        x_T = noise_fn = None
+        if glob is None:
+            post_noise = torch.randn(B, C_, T, F_)
+        else:                                 # sharded call: draw the global tensors, keep this rank's rows
+            Bg, rows = glob
+            post_noise = torch.randn(Bg, C_, T, F_)[rows[:B]]
+            noise_fn = parallel.ShardedNoise(Bg * n_gen, 0, 0, (C_, T, F_), self.device, rows=rows,
+                                             generator=torch.cuda.default_generators[self.device.index or 0])
+            x_T = noise_fn.x_T()
         mask = x0 = None
         if masked:
             fbank = torch.as_tensor(batch["log_mel_spec"], dtype=torch.float32)           # [B, T', F']
@@ -150,11 +177,12 @@ class NativeAudioLDM2:
             mask[:, int(T * tmask[0]):int(T * tmask[1]), :] = 0
             mask[:, :, int(F_ * fmask[0]):int(F_ * fmask[1])] = 0
             mask = mask[:, None].contiguous()
-        cond = _tile(self.cond_provider.cond(batch), n_gen)
+        cond = _tile(cond_rows if cond_rows is not None else self.cond_provider.cond(batch), n_gen)
         if guidance != 1.0 and uncond is None:
             uncond = self.cond_provider.uncond(Bl)                                        # ddpm.py:1529-1536
         texts = list(batch["text"]) * n_gen
-        wave = eng.generate_waveform(cond, uncond, ddim_steps=ddim_steps, guidance=guidance, eta=ddim_eta, mask=mask, x0=x0)
+        wave = eng.generate_waveform(cond, uncond, ddim_steps=ddim_steps, guidance=guidance, eta=ddim_eta, mask=mask, x0=x0,
+                                     x_T=x_T, noise_fn=noise_fn)
         waveform = self._egress(wave)                                                     # ddpm.py:936
         if n_gen > 1:
             if self.ranker is None:

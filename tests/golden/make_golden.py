@@ -189,6 +189,7 @@ def main():
         # round 2: the benchmark shape (B = 8), the other BASELINE configs at full size, a full-size masked run
         "unet_full_b8": lambda: gen_unet(R, "unet_full_b8", full, 8),
         "ddim_full_10_b8": lambda: gen_ddim(R, "ddim_full_10_b8", full, 8, 10, with_audio=True, audio_rows=[0, 7]),
+        "ddim_full_200_b8": lambda: gen_ddim(R, "ddim_full_200_b8", full, 8, 200, with_audio=True, audio_rows=[0, 7]),
         "ddim_full_10_masked": lambda: gen_ddim(R, "ddim_full_10_masked", full, 1, 10, masked=True, with_audio=True),
         "unet_48k_full": lambda: gen_unet(R, "unet_48k_full", m48, 1),
         "vae_48k_full": lambda: gen_vae(R, "vae_48k_full", m48, 1),
@@ -199,7 +200,7 @@ def main():
     for k, fn in jobs.items():
         if a.only and k != a.only:
             continue
-        if a.skip_200 and k == "ddim_full_200":
+        if a.skip_200 and k in ("ddim_full_200", "ddim_full_200_b8"):
             continue
         print(k)
         fn()

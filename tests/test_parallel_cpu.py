@@ -65,3 +65,36 @@ def test_two_rank_gloo():
     assert all(ok for _, ok, _, _ in res)
     assert sum(l for _, _, l, _ in res) == sum(range(10))
     assert all(t == 2.0 for _, _, _, t in res)
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend="gloo")
+    n = 5                                              # uneven shards: 3 + 2
+    r, w, lo, hi = parallel.current_shard(n)
+    full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 1, 3)
+    got = parallel.all_gather_rows(full[lo:hi].clone(), n)
+    # strided candidate rows of the prompts this rank owns (rows i + k*B, ddpm.py:1560-1562): same values as the full draw
+    B, n_gen = n, 2
+    rows = [i + k * B for k in range(n_gen) for i in range(lo, hi)]
+    sn = parallel.ShardedNoise(B * n_gen, 0, 0, (2, 2), "cpu", seed=9, rows=rows)
+    ref = parallel.ShardedNoise(B * n_gen, 0, B * n_gen, (2, 2), "cpu", seed=9)
+    ok_noise = bool(torch.equal(sn.x_T(), ref.x_T()[rows]) and torch.equal(sn(0, "step"), ref(0, "step")[rows]))
+    q.put((rank, bool(torch.equal(got, full)), ok_noise, (lo, hi)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_prompt_shards_gather_and_strided_noise_rows():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert all(ok and okn for _, ok, okn, _ in res)
+    assert [s for *_, s in res] == [(0, 3), (3, 5)]
