@@ -29,6 +29,13 @@ while [ $# -gt 0 ]; do
     bench)
       timeout 1500 python bench.py $BENCH_ARGS > gpurun_out/bench_$TAG.log 2>&1
       echo "== bench rc=$?"; grep '^{"metric"' gpurun_out/bench_$TAG.log > gpurun_out/bench_$TAG.json; tail -c 1500 gpurun_out/bench_$TAG.log ;;
+    configs)      # BASELINE configs C3 / C4 (one GPU's share) / C5, short runs
+      for c in "c3:--model audioldm_48k" "c4:--model audioldm2-full-large-1150k --no-torch-cuda-baseline" \
+               "c5:--model audioldm_48k --mode sr_inpainting --batch 2"; do
+        name=${c%%:*}; args=${c#*:}
+        timeout 900 python bench.py --steps 1 --warmup 1 --no-cpu-baseline $args > gpurun_out/bench_${name}_$TAG.log 2>&1
+        echo "== bench $name rc=$?"; grep '^{"metric"' gpurun_out/bench_${name}_$TAG.log > gpurun_out/bench_${name}_$TAG.json; tail -c 600 gpurun_out/bench_${name}_$TAG.log
+      done ;;
     refarm)
       timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1
       echo "== reference arm rc=$?"; tail -c 1200 gpurun_out/bench_ref_$TAG.log ;;

@@ -391,3 +391,19 @@ def test_48k_full_size_vs_reference():
     from audioldm2_b200 import frontend
     got = engine.stft_mel(cases.wav_input(491520).to(DEV).contiguous(), 2048, 480, frontend.mel_basis_for(cfg).to(DEV))
     _check("stft_48k logmel", rel_l2(got[0].t(), gs["logmel"][0]), NET_TOL)
+
+
+def test_end_to_end_batch8_200_steps_vs_reference(full_b8):
+    """The benchmark workload itself (config C2): batch 8, 200 DDIM steps, against the reference modules' CPU fp32 run."""
+    cfg = arch.model_config("audioldm2-full")
+    g = cases.load("ddim_full_200_b8")
+    _, _, cond, unc = cases.unet_inputs(cfg, 8)
+    x_T, noises, _ = cases.sampler_noise(cfg, 8, 200)
+    nf = lambda i, kind: noises[i].to(DEV)
+    z = full_b8.generate_latent(_to(cond, DEV), _to(unc, DEV), ddim_steps=200, guidance=3.5, eta=1.0, x_T=x_T, noise_fn=nf)
+    _check("b8/200 latent", rel_l2(z, g["latent"]), WAVE_TOL)
+    rows = g["audio_rows"].tolist()
+    mel = full_b8.decode_first_stage(z)
+    wave = full_b8.mel_spectrogram_to_waveform(mel)
+    _check("b8/200 mel", rel_l2(mel[rows], g["mel"]), WAVE_TOL)
+    _check("b8/200 waveform", rel_l2(wave[rows], g["wave"]), WAVE_TOL)
