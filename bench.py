@@ -116,7 +116,13 @@ class ClockSampler:
 # CPU arm: the reference's own modules (baseline/_ref) or the oracle port on the host cores.  Clips are independent,
 # so the host is filled with W worker processes x T intra-op threads, each sampling B = 1.
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(conn, model_name, t5_len, threads, seed):
+def _cpu_worker(conn, model_name, t5_len, threads, seed, cpus):
+    # one block of logical CPUs per worker: without it the OpenMP runtimes of all workers may bind to the SAME cores
+    # (measured on the 128-thread GPU-box host: 8 workers x 16 threads ran 10x slower than one worker alone)
+    try:
+        os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
     torch.set_num_threads(threads)
     from oracle import ref_bench
     ref = ref_bench.ReferencePath(model_name, 1, "cpu", t5_len=t5_len)
@@ -139,14 +145,19 @@ def _cpu_worker(conn, model_name, t5_len, threads, seed):
 class CpuPool:
     def __init__(self, model_name: str, t5_len: int):
         import torch.multiprocessing as mp
-        n = os.cpu_count() or 1
+        try:
+            allowed = sorted(os.sched_getaffinity(0))
+        except Exception:
+            allowed = list(range(os.cpu_count() or 1))
+        n = len(allowed)
         self.threads = int(os.environ.get("ALDM_CPU_THREADS", min(16, n)))
         self.workers = int(os.environ.get("ALDM_CPU_WORKERS", max(1, n // self.threads)))
         ctx = mp.get_context("spawn")
         self.conns, self.procs = [], []
         for w in range(self.workers):
             a, b = ctx.Pipe()
-            p = ctx.Process(target=_cpu_worker, args=(b, model_name, t5_len, self.threads, 1000 + w), daemon=True)
+            cpus = set(allowed[(w * self.threads) % n:(w * self.threads) % n + self.threads]) or set(allowed)
+            p = ctx.Process(target=_cpu_worker, args=(b, model_name, t5_len, self.threads, 1000 + w, cpus), daemon=True)
             p.start()
             self.conns.append(a); self.procs.append(p)
         infos = [c.recv() for c in self.conns]
