@@ -208,7 +208,6 @@ def lib() -> C.CDLL:
         "aldm_last_error": (C.c_char_p, []),
         "aldm_device_check": (i32, [i32]),
         "aldm_debug_timeline": (i32, [vp, i32]),
-        "aldm_gemm_tile_rows": (i32, [C.POINTER(GemmDesc)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the symbol is not exported
@@ -232,7 +231,7 @@ EXPORTED = ["aldm_gemm", "aldm_prep", "aldm_pack_b", "aldm_attention", "aldm_sof
             "aldm_engine_destroy", "aldm_engine_set_conditioning", "aldm_engine_precompute", "aldm_engine_unet_eps",
             "aldm_engine_ddim_step", "aldm_engine_vae_decode", "aldm_engine_vocoder", "aldm_engine_vae_encode",
             "aldm_sizeof_engine_desc", "aldm_abi_version", "aldm_sizeof_op",
-            "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check", "aldm_debug_timeline", "aldm_gemm_tile_rows"]
+            "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check", "aldm_debug_timeline"]
 
 
 def check(rc: int, what: str = ""):

@@ -283,22 +283,21 @@ __device__ __forceinline__ void emit_rows(const aldm_gemm_desc& d, const CR& cr,
 // ------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, int AP, int MS>
+template <int BN, int AP>
 struct Tc3Cfg {
-  static constexpr int BM = 128 * MS;                 // MS M sub-tiles of 128 rows share every B stage
+  static constexpr int BM = 128;
   static constexpr int BK = 64;                       // fp16 elements = 128 bytes per row
-  static constexpr int A_BYTES = BM * 128;            // one plane (all sub-tiles, rows contiguous)
+  static constexpr int A_BYTES = BM * 128;            // one plane
   static constexpr int B_BYTES = BN * 128;            // one plane
   static constexpr int STAGE_BYTES = AP * A_BYTES + 2 * B_BYTES;      // [a_hi | a_lo (AP == 2)] [b_hi | b_lo]
   static constexpr int B_OFF = AP * A_BYTES;
   static constexpr int STG_BYTES = 8 * 32 * 33 * 4;   // one 32x33 fp32 transpose tile per epilogue warp
   static constexpr int SMEM_MAX = 227 * 1024;
   static constexpr int FIT = (SMEM_MAX - 1024 - 256 - STG_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = FIT > 4 ? 4 : FIT;    // BN=128: MS=1: 3 (AP=2, 64 KB stages) / 4 (AP=1, 48 KB); MS=2: 2 (96 KB) / 3 (64 KB)
+  static constexpr int STAGES = FIT > 4 ? 4 : FIT;    // BN=128: 3 (AP=2, 64 KB stages) / 4 (AP=1, 48 KB)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
-  static constexpr int TMEM_COLS = MS * BN;           // columns of ONE accumulator set (MS sub-tiles side by side); two sets are allocated
+  static constexpr int TMEM_COLS = BN;                // power of two >= 32
   static_assert(STAGES >= 2, "pipeline needs two stages");
-  static_assert(2 * TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM: 512 columns, power-of-two allocation");
 };
 
 // Debug timeline (profiling aid, dbg bit 128): CTA 0 records clock64() at pipeline events.
@@ -357,14 +356,10 @@ struct Tc3Divs {
 };
 
 // AP = number of A planes (2: hi + lo, three UMMAs per K step; 1: hi only, two UMMAs and half the A bytes).
-// MS = M sub-tiles per CTA tile (1: 128 x BN; 2: 256 x BN, two accumulators side by side in TMEM fed from ONE B stage).
-// The kernel is bound by L2 -> SM operand traffic wherever all SMs stream at once (~7.7 TB/s in aggregate on the B200:
-// time follows bytes per k-block exactly, profiles/r02_prof_ops_planes*.txt); a 256-row tile moves 64 KB (AP = 1) per two
-// 128 x 128 x 64 units instead of 96 KB.
-template <int BN, int EPI, int AP, int MS>
+template <int BN, int EPI, int AP>
 __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant__ aldm_gemm_desc d, int tiles_m, int tiles_n,
                                                            const __grid_constant__ Tc3Divs fd) {
-  using C = Tc3Cfg<BN, AP, MS>;
+  using C = Tc3Cfg<BN, AP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -430,22 +425,20 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     const aldm_plane_t* alo = reinterpret_cast<const aldm_plane_t*>(d.a_lo);
     uint32_t cnt = 0;
     int last_mt = -1;
-    constexpr int NR = 8 * MS;        // rows of the tile this thread gathers: rbase + 16 i
-    constexpr int NUP = MS == 1 ? 8 : 1;      // the nearest-upsample path exists for 128-row tiles only (host-checked)
-    int rowoff[NR];           // element offset of tap (0,0) / channel 0 of each row (valid rows only)
-    uint32_t tapmask[NR];     // bit t set <=> tap t of this row is inside the input
-    int ih0[NUP], iw0[NUP], pbh[NUP];   // only used by the nearest-upsample (up = 1) slow path
+    int rowoff[8];            // element offset of tap (0,0) / channel 0 of each row (valid rows only)
+    uint32_t tapmask[8];      // bit t set <=> tap t of this row is inside the input
+    int ih0[8], iw0[8], pbh[8];   // only used by the nearest-upsample (up = 1) slow path
     // Row decode of one M tile.  A single warp per scheduler runs this dependent integer chain at ~1 instruction
     // per 6-8 cycles, and the timeline showed ~5,000 idle tensor-core cycles at every tile boundary of the K = 256
     // linear layers because of it: linear layers take the trivial branch, and the first tile is decoded before the
     // programmatic-dependency wait (under the previous kernel's tail).
     auto decode_rows = [&](int mt) {
 #pragma unroll
-      for (int i = 0; i < NR; ++i) {
+      for (int i = 0; i < 8; ++i) {
         const int m = mt * C::BM + rbase + 16 * i;
         uint32_t msk = 0;
         int off = 0;
-        if (MS == 1) { ih0[i % NUP] = 0; iw0[i % NUP] = 0; pbh[i % NUP] = -1; }
+        ih0[i] = 0; iw0[i] = 0; pbh[i] = -1;
         if (fd.plain) {
           if (m < M) { msk = 1u; off = m * d.Cp; }
         } else if (m < M) {
@@ -456,7 +449,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           int bs = b;
           if (d.bmod > 0) { int q; fd.bmod.divmod(b, q, bs); }
           const int pb = bs * Hs;
-          if (MS == 1) { ih0[i % NUP] = y0; iw0[i % NUP] = x0; pbh[i % NUP] = pb; }
+          ih0[i] = y0; iw0[i] = x0; pbh[i] = pb;
           for (int tp = 0; tp < d.ntaps; ++tp) {
             const int ih = y0 + d.dy[tp], iw = x0 + d.dx[tp];
             if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) msk |= 1u << tp;
@@ -492,10 +485,10 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         const bool kvalid = tap < d.ntaps;
         const int tp = kvalid ? tap : 0;
         const uint32_t sa = base + s * C::STAGE_BYTES + swz;
-        if (MS > 1 || d.up == 0) {
+        if (d.up == 0) {
           const int tapoff = (d.dy[tp] * Ws + d.dx[tp]) * d.Cp + c;
 #pragma unroll
-          for (int i = 0; i < NR; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const bool ok = kvalid && ((tapmask[i] >> tp) & 1u);
             const long long off = ok ? (long long)(rowoff[i] + tapoff) : 0ll;
             const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
@@ -507,7 +500,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         } else {      // nearest x2 upsample folded into the gather: source pixel = (ih >> 1, iw >> 1)
           const int dy = d.dy[tp], dx = d.dx[tp];
 #pragma unroll
-          for (int i = 0; i < NUP; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const bool ok = kvalid && ((tapmask[i] >> tp) & 1u);
             long long off = 0;
             if (ok) off = ((long long)(pbh[i] + ((ih0[i] + dy) >> 1)) * Ws + ((iw0[i] + dx) >> 1)) * d.Cp + c;
@@ -553,28 +546,24 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         const uint32_t acc = tl & 1;
         mbar_wait(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tmem_base + acc * C::TMEM_COLS;
+        const uint32_t tacc = tmem_base + acc * BN;
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
           mbar_wait(full_bar(s), (cnt / C::STAGES) & 1);
           ALDM_TL(2, cnt, 0);
           tc_fence_after();
           const uint32_t sa = base + s * C::STAGE_BYTES;
+          const uint64_t da_hi = umma_desc_sw128(sa);
+          const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);      // only used when AP == 2
           const uint64_t db_hi = umma_desc_sw128(sa + C::B_OFF);
           const uint64_t db_lo = umma_desc_sw128(sa + C::B_OFF + C::B_BYTES);
           if (!(dbg & 4)) {
 #pragma unroll
-            for (int ms = 0; ms < MS; ++ms) {           // M sub-tiles: rows [128 ms, 128 ms + 128) of the A stage, accumulator columns [ms BN, ..)
-              const uint64_t da_hi = umma_desc_sw128(sa + ms * (128 * 128));
-              const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES + ms * (128 * 128));      // only used when AP == 2
-              const uint32_t tsub = tacc + ms * BN;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {          // 4 x K=16 (32 bytes) inside the 128B swizzle row
-                const uint64_t o = (uint64_t)(ks * 2);
-                if (AP == 2) umma_f16(tsub, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
-                umma_f16(tsub, da_hi + o, db_lo + o, idesc, AP == 2 ? 1u : (uint32_t)((it | ks) != 0));     // small terms first
-                umma_f16(tsub, da_hi + o, db_hi + o, idesc, 1);
-              }
+            for (int ks = 0; ks < 4; ++ks) {            // 4 x K=16 (32 bytes) inside the 128B swizzle row
+              const uint64_t o = (uint64_t)(ks * 2);
+              if (AP == 2) umma_f16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
+              umma_f16(tacc, da_hi + o, db_lo + o, idesc, AP == 2 ? 1u : (uint32_t)((it | ks) != 0));     // small terms first
+              umma_f16(tacc, da_hi + o, db_hi + o, idesc, 1);
             }
           }
           umma_commit(empty_bar(s));
@@ -596,9 +585,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
       int mt, nt, z, kb0, nkb;
       tile_coords(id, mt, nt, z, kb0, nkb);
       const uint32_t acc = tl & 1;
-#pragma unroll 1
-      for (int ms = 0; ms < MS; ++ms) {
-      const int m = mt * C::BM + ms * 128 + trow_in_tile;
+      const int m = mt * C::BM + trow_in_tile;
       RowInfo r;
       {
         r.m = m; r.valid = m < M;
@@ -626,12 +613,10 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         }
         if (has_res && half * 32 < BN) co_load_res32(d, cr32, nt * BN + half * 32, d.N, lane, prv[0]);
       }
-      if (ms == 0) {
-        mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
-        if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
-        tc_fence_after();
-      }
-      const uint32_t trow = tmem_base + acc * C::TMEM_COLS + ms * BN + ((uint32_t)(lb * 32) << 16);
+      mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
+      if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(lb * 32) << 16);
       if (dbg & 8) {
         // skip
       } else if (d.splitk > 1) {
@@ -649,7 +634,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rs;
-            float* wp = d.ws + ((long long)z * Mpad + mt * C::BM + ms * 128 + lb * 32 + rr) * Npad + nt * BN + c0 + c4;
+            float* wp = d.ws + ((long long)z * Mpad + mt * C::BM + lb * 32 + rr) * Npad + nt * BN + c0 + c4;
             *reinterpret_cast<float4*>(wp) = make_float4(stg[rr * 33 + c4], stg[rr * 33 + c4 + 1], stg[rr * 33 + c4 + 2], stg[rr * 33 + c4 + 3]);
           }
           __syncwarp();
@@ -750,7 +735,6 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           }
         }
       }
-      }   // M sub-tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -907,24 +891,19 @@ __global__ void gemm_simt_kernel(const __grid_constant__ aldm_gemm_desc d, int N
 // ------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
-template <int BN, int EPI, int AP, int MS>
-static int launch_tc3_ms(const aldm_gemm_desc& d, int M, cudaStream_t st) {
-  using C = Tc3Cfg<BN, AP, MS>;
+template <int BN, int EPI, int AP>
+static int launch_tc3_ap(const aldm_gemm_desc& d, int M, cudaStream_t st) {
+  using C = Tc3Cfg<BN, AP>;
   static bool configured = false;
   if (!configured) {
-    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, EPI, AP, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    ALDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<BN, EPI, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  num_sms();
+  if (g_num_sms == 0) {
+    int dev = 0;
+    ALDM_CHECK_CUDA(cudaGetDevice(&dev));
+    ALDM_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   const int tiles_m = cdiv(M, C::BM), tiles_n = cdiv(d.N, BN);
   const long long total = (long long)tiles_m * tiles_n * d.splitk;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
@@ -933,7 +912,7 @@ static int launch_tc3_ms(const aldm_gemm_desc& d, int M, cudaStream_t st) {
   fd.bmod = make_fastdiv(d.bmod > 0 ? d.bmod : 1);
   fd.plain = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.sy == 1 && d.sx == 1 && d.up == 0 && d.bmod <= 0 &&
              d.OH == d.H && d.OW == d.W;
-  ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI, AP, MS>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd));
+  ALDM_CHECK_CUDA(launch_pdl(gemm_tc3_kernel<BN, EPI, AP>, dim3(grid), dim3(448), C::SMEM_BYTES, st, d, tiles_m, tiles_n, fd));
   ALDM_CHECK_CUDA(cudaGetLastError());
   if (d.splitk > 1) {
     const int Mpad = tiles_m * C::BM, Npad = tiles_n * BN;
@@ -953,26 +932,6 @@ static int launch_tc3_ms(const aldm_gemm_desc& d, int M, cudaStream_t st) {
     ALDM_CHECK_CUDA(cudaGetLastError());
   }
   return ALDM_OK;
-}
-
-// 256-row tiles (MS = 2) move a third (AP = 1) / a quarter (AP = 2) fewer operand bytes per FLOP; they are taken when the
-// GEMM still fills the machine with them and loses nothing to wave quantisation against 128-row tiles.  ALDM_GEMM_MS2=0
-// disables them (A/B switch).
-static bool ms2_pays(const aldm_gemm_desc& d, int M, int BN) {
-  static const bool on = [] { const char* e = getenv("ALDM_GEMM_MS2"); return !(e && e[0] == '0'); }();
-  if (!on || BN != 128 || d.up != 0 || d.splitk != 1 || M < 256) return false;
-  const int sms = num_sms(), tn = cdiv(d.N, BN);
-  const long long t256 = (long long)cdiv(M, 256) * tn, t128 = (long long)cdiv(M, 128) * tn;
-  auto eff = [&](long long t) { return (double)t / (double)(((t + sms - 1) / sms) * sms); };
-  return t256 >= (3 * sms) / 4 && eff(t256) >= eff(t128) - 0.05;
-}
-
-template <int BN, int EPI, int AP>
-static int launch_tc3_ap(const aldm_gemm_desc& d, int M, cudaStream_t st) {
-  if constexpr (BN == 128) {
-    if (ms2_pays(d, M, BN)) return launch_tc3_ms<BN, EPI, AP, 2>(d, M, st);
-  }
-  return launch_tc3_ms<BN, EPI, AP, 1>(d, M, st);
 }
 
 template <int BN, int EPI>
@@ -1060,13 +1019,6 @@ extern "C" int aldm_debug_timeline(long long* host_out, int32_t n) {
   ALDM_REQUIRE(host_out && n > 0 && n <= 4 * 256 * 2, ALDM_E_ARG, "debug_timeline: bad arguments");
   ALDM_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * n));
   return ALDM_OK;
-}
-
-extern "C" int aldm_gemm_tile_rows(const aldm_gemm_desc* d) {
-  if (!d) return 0;
-  if ((d->impl & 0xff) == ALDM_GEMM_SIMT) return 1;
-  const long long M = (long long)d->B * d->OH * d->OW;
-  return aldm::ms2_pays(*d, (int)M, d->bn) ? 256 : 128;
 }
 
 extern "C" int aldm_gemm(const aldm_gemm_desc* d, void* stream) {

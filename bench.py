@@ -163,11 +163,31 @@ class CpuPool:
         infos = [c.recv() for c in self.conns]
         self.kind, self.where = infos[0][1], infos[0][2]
         self.t_dec = None
+        self.active = self.workers
+        self.calibration = None
+
+    def calibrate(self, S: int):
+        """How many of the spawned workers to run at once.  The logical-CPU count of a container says nothing about its CPU
+        quota (the GPU box reports 128 logical CPUs; 8 concurrent 16-thread workers each ran 10x slower than one alone), so
+        the whole-host throughput of 1, 2, 4, ... concurrent workers is measured on one DDIM step and the best count kept."""
+        trials, k = {}, 1
+        while True:
+            self.active = min(k, self.workers)
+            ps = self.run(S, 1, False)
+            trials[self.active] = sum(1.0 / p for p in ps)
+            if self.active == self.workers:
+                break
+            k *= 2
+        self.active = max(trials, key=trials.get)
+        self.calibration = {str(a): round(v, 4) for a, v in trials.items()}      # DDIM steps / s of the whole host
+        if self.t_dec is not None:
+            self.t_dec = self.t_dec[:self.active]
 
     def run(self, S: int, n_steps: int, with_decode: bool):
-        for c in self.conns:
+        conns = self.conns[:self.active]
+        for c in conns:
             c.send((S, n_steps, with_decode))
-        res = [c.recv() for c in self.conns]
+        res = [c.recv() for c in conns]
         if with_decode:
             self.t_dec = [r[1] for r in res]
         return [r[0] / n_steps for r in res]             # seconds per DDIM step, per worker
@@ -176,10 +196,11 @@ class CpuPool:
         return sum(1.0 / (S * ps + td) for ps, td in zip(per_step, self.t_dec))
 
     def cores(self) -> int:
-        return self.workers * self.threads
+        return self.active * self.threads
 
     def describe(self, S, n_steps, per_step) -> str:
-        return (f"{self.workers} worker process(es) x {self.threads} threads (host has {os.cpu_count()} logical cores), each B=1: "
+        return (f"{self.active} concurrent worker process(es) x {self.threads} threads, pinned to disjoint CPU blocks (host reports "
+                f"{os.cpu_count()} logical CPUs; concurrency calibrated on whole-host DDIM steps/s: {self.calibration}), each B=1: "
                 f"{n_steps} real DDIM steps (2 UNet calls each; mean {sum(per_step) / len(per_step):.2f} s/step) + VAE decode + HiFi-GAN "
                 f"(mean {sum(self.t_dec) / len(self.t_dec):.2f} s, timed once), fp32 torch CPU, extrapolated to {S} steps per clip")
 
@@ -203,6 +224,8 @@ def run_reference_arm(a):
     n_t = min(10, S)
     pool = CpuPool(a.model, a.t5_len)
     try:
+        pool.run(S, 1, False)                                      # page in weights / thread pools
+        pool.calibrate(S)
         for _ in range(a.warmup):
             pool.run(S, min(2, S), pool.t_dec is None)            # first warm-up also times the decode
         if pool.t_dec is None:
@@ -213,7 +236,7 @@ def run_reference_arm(a):
             vals.append(pool.clips_per_s(S, last))
         v = sum(vals) / len(vals)
         line = dict(metric=metric_name(a), value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=1000.0 * pool.workers / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    ms_per_step=1000.0 * pool.active / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic", impl="reference",
                     config=dict(workload=workload(a, cfg),
                                 note="CPU arm: clips are independent, so each bench step times a bounded sample of this workload on every "
@@ -441,6 +464,8 @@ def main():
     if world == 1 and not a.no_cpu_baseline and not sr_mode:
         pool = CpuPool(a.model, a.t5_len)
         try:
+            pool.run(S, 1, False)
+            pool.calibrate(S)
             pool.run(S, 1, True)
             ps = pool.run(S, min(10, S), False)
             cpu = dict(value=pool.clips_per_s(S, ps), unit=UNIT, cores=pool.cores(), kind=pool.kind, where=pool.where,

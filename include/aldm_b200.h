@@ -319,7 +319,6 @@ size_t aldm_sizeof_engine_desc(void);
 size_t aldm_offsetof_gemm(int32_t field);     /* 0:B 1:ntaps 2:dy 3:N 4:ldo 5:act 6:alpha 7:n_split (layout self-check) */
 const char* aldm_last_error(void);
 int aldm_device_check(int32_t device);
-int aldm_gemm_tile_rows(const aldm_gemm_desc* d);           /* introspection: M rows per CTA tile the launcher picks (256 / 128; 1 = SIMT checker) */
 int aldm_debug_timeline(long long* host_out, int32_t n);   /* profiling aid: per-stage clock64 stamps of CTA 0 (scripts/prof_ops.py --timeline) */        /* 0 if `device` is sm_100 and kernels can load */
 
 #ifdef __cplusplus

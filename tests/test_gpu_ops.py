@@ -190,13 +190,9 @@ GEMM_CASES = {
     "a1_dual_p2": dict(B=1, H=300, W=1, Cin=1024, N=256, taps=((0, 0),), res=True, dual=True, a_planes=1),
     "a1_conv3x3": dict(B=2, H=20, W=6, Cin=24, N=128, taps=plan.TAPS_3x3, rowvec=True, res=True, a_planes=1),
     "a1_deepK_splitk": dict(B=2, H=8, W=2, Cin=640, N=640, taps=plan.TAPS_3x3, res=True, a_planes=1),
-    # 256-row CTA tiles (two M sub-tiles per B stage): taken when >= 111 such tiles exist; ragged last tile (second sub-tile empty)
-    "ms2_a1_linear_res": dict(B=1, H=30001, W=1, Cin=128, N=128, taps=((0, 0),), res=True, a_planes=1),
-    "ms2_conv3x3_rowvec": dict(B=8, H=64, W=64, Cin=32, N=128, taps=plan.TAPS_3x3, rowvec=True, res=True),
-    "ms2_a1_geglu_p1": dict(B=1, H=16384, W=1, Cin=64, N=2048, taps=((0, 0),), geglu=True, act=_lib.ACT_GEGLU, out_kind="planes",
-                            a_planes=1, out_planes_n=1),
-    "ms2_a1_dual": dict(B=1, H=30000, W=1, Cin=256, N=128, taps=((0, 0),), res=True, dual=True, a_planes=1),
-    "ms2_planes_p2": dict(B=1, H=29000, W=1, Cin=72, N=256, taps=((0, 0),), out_kind="planes"),
+    # many tiles per persistent CTA, ragged last tile
+    "a1_long_linear_res": dict(B=1, H=30001, W=1, Cin=128, N=128, taps=((0, 0),), res=True, a_planes=1),
+    "long_conv3x3_rowvec": dict(B=8, H=64, W=64, Cin=32, N=128, taps=plan.TAPS_3x3, rowvec=True, res=True),
 }
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
@@ -210,10 +206,6 @@ def test_gemm_vs_emulator(case, impl):
         assert pl.ops[-1]["splitk"] > 1
     if "a1_" in case:
         assert pl.ops[-1]["a_lo"] is None
-    if impl == "tc":
-        arr = pl.resolve(0x1000, 0x1000, len(pl.ops) - 1, len(pl.ops))
-        rows = _lib.lib().aldm_gemm_tile_rows(C.byref(arr[0].u.gemm))
-        assert rows == (256 if case.startswith("ms2_") else 128), (case, rows)
     em, prog = run_both(pl, ins)
     ptol = 3e-4 if GEMM_CASES[case].get("out_planes_n", 2) == 1 else 2e-5      # single plane: one-ulp flips of an 11-bit rounding
     if kind == "dual":
