@@ -47,6 +47,16 @@ while [ $# -gt 0 ]; do
     nettests)
       timeout 1500 python -m pytest tests/test_gpu_nets.py tests/test_gpu_zz_engine_abi.py -m gpu -q -s -p no:cacheprovider > gpurun_out/pytest_nets_$TAG.log 2>&1
       echo "== net tests rc=$?"; grep "rel L2\|passed\|failed\|FAILED\|Error" gpurun_out/pytest_nets_$TAG.log | tail -60 ;;
+    ncu-full)     # one --set full capture per dominant op shape (scripts/prof_ops.py cases) + the small HBM kernels
+      for c in ${NCU_CASES:-lin_k1024_n256 lin_k256_n2048_geglu lin_k640_n640 conv_l2_256 attn_1024 ln_16384x256 gn_silu_l1}; do
+        case $c in attn*) pat='attention_tc';; ln*) pat='ln_kernel';; gn*) pat='gn_apply_col';; *) pat='gemm_tc3';; esac
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s 1 -c 1 -f -o gpurun_out/ncu_${TAG}_$c \
+          python scripts/prof_ops.py --reps 2 --only $c > gpurun_out/ncu_${TAG}_$c.log 2>&1
+        echo "== ncu $c rc=$?"
+      done
+      timeout 600 ncu --set full --clock-control none -k regex:'ddim_step|stft_mel' -c 3 -f -o gpurun_out/ncu_${TAG}_small \
+        python scripts/prof_small.py 2 > gpurun_out/ncu_${TAG}_small.log 2>&1
+      echo "== ncu small rc=$?" ;;
     ncu-list)
       timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
         --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 0 --ddim-steps 2 --no-graph --no-cpu-baseline \
