@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaldm_b200.so")
-SOURCES = ["gemm.cu", "prep.cu", "attention.cu", "elementwise.cu", "stft.cu", "program.cu", "engine_abi.cu"]
+SOURCES = ["gemm.cu", "prep.cu", "attention.cu", "elementwise.cu", "stft.cu", "program.cu", "engine_abi.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -208,6 +208,7 @@ def lib() -> C.CDLL:
         "aldm_last_error": (C.c_char_p, []),
         "aldm_device_check": (i32, [i32]),
         "aldm_debug_timeline": (i32, [vp, i32]),
+        "aldm_debug_umma_rate": (i32, [i32, i32, i32, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the symbol is not exported
@@ -231,7 +232,8 @@ EXPORTED = ["aldm_gemm", "aldm_prep", "aldm_pack_b", "aldm_attention", "aldm_sof
             "aldm_engine_destroy", "aldm_engine_set_conditioning", "aldm_engine_precompute", "aldm_engine_unet_eps",
             "aldm_engine_ddim_step", "aldm_engine_vae_decode", "aldm_engine_vocoder", "aldm_engine_vae_encode",
             "aldm_sizeof_engine_desc", "aldm_abi_version", "aldm_sizeof_op",
-            "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check", "aldm_debug_timeline"]
+            "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check", "aldm_debug_timeline",
+            "aldm_debug_umma_rate"]
 
 
 def check(rc: int, what: str = ""):

@@ -121,17 +121,27 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       float mnew, corr, psum = 0.f;
       if (k0 + KT <= d.Nk && !mrow) {
         // interior tile, no mask: max on the raw scores (sl2 > 0), one FFMA + one MUFU per element
-        float tmax = s[0];
+        // four independent max / sum chains: a single chain of 64 dependent operations (4-cycle latency each) left the
+        // two softmax warps per scheduler waiting on themselves for ~500 cycles per key tile
+        float t4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int j = 1; j < KT; ++j) tmax = fmaxf(tmax, s[j]);
+        for (int j = 4; j < KT; j += 4) {
+          t4[0] = fmaxf(t4[0], s[j]); t4[1] = fmaxf(t4[1], s[j + 1]); t4[2] = fmaxf(t4[2], s[j + 2]); t4[3] = fmaxf(t4[3], s[j + 3]);
+        }
+        const float tmax = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
         mnew = fmaxf(mrun, tmax * sl2);
         corr = ex2_approx(mrun - mnew);                  // mrun = -inf on the first tile -> 0
+        float p4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < KT; ++j) {
-          const float p = ex2_approx(fmaf(s[j], sl2, -mnew));
-          s[j] = p;
-          psum += p;
+        for (int j = 0; j < KT; j += 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p = ex2_approx(fmaf(s[j + e], sl2, -mnew));
+            s[j + e] = p;
+            p4[e] += p;
+          }
         }
+        psum = (p4[0] + p4[1]) + (p4[2] + p4[3]);
       } else {
         float tmax = -INFINITY;
 #pragma unroll
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
     }
   } else {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idS = umma_idesc_f16(128, KT), idO = umma_idesc_f16(128, ATT_D);
       const uint64_t dQ = umma_desc_sw128(base + QA);
       const uint64_t dP = umma_desc_sw128(base + PP);

@@ -126,6 +126,36 @@ __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;     // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
 }
 
+// v[i] *= gelu(g[i]) for NB values at once, written stage by stage so that NB independent dependency chains are in
+// flight: the GEGLU epilogue runs two warps per scheduler, and with the elements evaluated one or two at a time
+// (what the compiler produced from the scalar form under the 128-register cap) the ~75-cycle chain of each element
+// (two MUFU round trips) was fully exposed: 3,900 cycles per 32 x 32 chunk in the timeline, 7,000 per tile.
+template <int NB>
+__device__ __forceinline__ void geglu_mul(float* __restrict__ v, const float* __restrict__ g) {
+  float z[NB], t[NB], e[NB], p[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) z[j] = fabsf(g[j]) * 0.70710678118654752440f;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(fmaf(0.3275911f, z[j], 1.0f)));
+#pragma unroll
+  for (int j = 0; j < NB; ++j) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(-z[j] * z[j] * 1.4426950408889634f));
+#pragma unroll
+  for (int j = 0; j < NB; ++j) p[j] = fmaf(1.061405429f, t[j], -1.453152027f);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) p[j] = fmaf(p[j], t[j], 1.421413741f);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) p[j] = fmaf(p[j], t[j], -0.284496736f);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) p[j] = fmaf(p[j], t[j], 0.254829592f);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) p[j] *= t[j] * e[j];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const float erf_abs = 1.0f - p[j];
+    v[j] *= fmaf(0.5f * fabsf(g[j]), erf_abs, 0.5f * g[j]);      // 0.5 g (1 + sign(g) erf(|g| / sqrt 2))
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // shared-memory address + mbarrier
 // ------------------------------------------------------------------------------------------
@@ -207,6 +237,11 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// same with an immediate destination offset (one base register for the eight rows a producer thread copies per k-block)
+template <int OFF>
+__device__ __forceinline__ void cp_async_16_off(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0 + %3], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes), "n"(OFF) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -228,6 +263,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tenso
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// One elected lane of a fully converged warp.  The single-thread roles (tcgen05.mma / commit issue, TMA bulk copies) must
+// be entered through THIS predicate, not `lane == 0`: the instructions take their operands from uniform registers, and
+// under a lane-id predicate the compiler cannot prove uniformity, so it wraps EVERY such instruction in an
+// ELECT / BRA.U.ANY loop -- measured at ~95 cycles per tcgen05.mma (csrc/microbench.cu) against 64 cycles of tensor
+// work for a 128 x 128 x 16 step, i.e. the issue loop, not the tensor core, paced every GEMM and the attention kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -274,6 +320,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// Accumulator read of the GEMM: the tile lives in TMEM as two column blocks DIST apart -- [A W_hi^T (+ A_lo W_hi^T) | A W_lo^T],
+// written by ONE N = 2 BN tcgen05.mma per K step (gemm.cu) -- and the value is their sum.  The second block is read in two
+// 16-column pieces so that at most 48 registers are live.  Includes the tcgen05.wait::ld.
+template <int DIST, bool STACKED>
+__device__ __forceinline__ void acc_ld32(uint32_t taddr, uint32_t* r) {
+  if (!STACKED) {
+    tmem_ld32(taddr, r);
+    tmem_ld_wait();
+    return;
+  }
+  uint32_t t[16];
+  tmem_ld32(taddr, r);
+  tmem_ld16(taddr + DIST, t);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t[i]));
+  tmem_ld16(taddr + DIST + 16, t);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[16 + i] = __float_as_uint(__uint_as_float(r[16 + i]) + __uint_as_float(t[i]));
+}
 
 // K-major, 128-byte-swizzled operand tile descriptor (rows of 128 B, 8-row groups 1024 B apart).
 // Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),

@@ -296,7 +296,13 @@ struct Tc3Cfg {
   static constexpr int FIT = (SMEM_MAX - 1024 - 256 - STG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 4 ? 4 : FIT;    // BN=128: 3 (AP=2, 64 KB stages) / 4 (AP=1, 48 KB)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
-  static constexpr int TMEM_COLS = BN;                // power of two >= 32
+  // ST ("stacked"): the B stage [W_hi rows | W_lo rows] is issued as ONE N = 2 BN operand, so the accumulator is two column
+  // blocks [A W_hi^T (+ A_lo W_hi^T) | A W_lo^T] that the epilogue adds.  Used for the two-plane (convolution) operands, whose
+  // long K loops are tensor-bound: 2 instead of 3 instructions per K step (measured 273 vs 314 cycles, csrc/microbench.cu).  The
+  // single-plane token-side GEMMs keep the plain form: their short K loops are epilogue-bound and the second TMEM read of the
+  // stacked form made them slower (lin_k256_n768_qkv 34.6 -> 44.6 us), while their MMA time hides under the epilogue anyway.
+  static constexpr bool ST = AP == 2;
+  static constexpr int TMEM_COLS = ST ? 2 * BN : BN;  // one accumulator (power of two >= 32)
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
 
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     uint32_t cnt = 0;
     int last_mt = -1;
     int rowoff[8];            // element offset of tap (0,0) / channel 0 of each row (valid rows only)
-    uint32_t tapmask[8];      // bit t set <=> tap t of this row is inside the input
+    uint32_t tapmask[8];      // bit (t + 4) set <=> tap t of this row is inside the input (pre-shifted: (mask >> t) & 16 = bytes to copy)
     int ih0[8], iw0[8], pbh[8];   // only used by the nearest-upsample (up = 1) slow path
     // Row decode of one M tile.  A single warp per scheduler runs this dependent integer chain at ~1 instruction
     // per 6-8 cycles, and the timeline showed ~5,000 idle tensor-core cycles at every tile boundary of the K = 256
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         int off = 0;
         ih0[i] = 0; iw0[i] = 0; pbh[i] = -1;
         if (fd.plain) {
-          if (m < M) { msk = 1u; off = m * d.Cp; }
+          if (m < M) { msk = 16u; off = m * d.Cp; }
         } else if (m < M) {
           int t, ow, b, oh;
           fd.ow.divmod(m, t, ow);
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           ih0[i] = y0; iw0[i] = x0; pbh[i] = pb;
           for (int tp = 0; tp < d.ntaps; ++tp) {
             const int ih = y0 + d.dy[tp], iw = x0 + d.dx[tp];
-            if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) msk |= 1u << tp;
+            if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) msk |= 16u << tp;
           }
           off = ((pb + y0) * Ws + x0) * d.Cp;
         }
@@ -485,23 +491,47 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         const bool kvalid = tap < d.ntaps;
         const int tp = kvalid ? tap : 0;
         const uint32_t sa = base + s * C::STAGE_BYTES + swz;
-        if (d.up == 0) {
-          const int tapoff = (d.dy[tp] * Ws + d.dx[tp]) * d.Cp + c;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = kvalid && ((tapmask[i] >> tp) & 1u);
-            const long long off = ok ? (long long)(rowoff[i] + tapoff) : 0ll;
-            const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
-            if (!(dbg & 1)) {
-              cp_async_16(dst, ahi + off, ok ? 16u : 0u);
-              if (AP == 2) cp_async_16(dst + C::A_BYTES, alo + off, ok ? 16u : 0u);
+        // Per 16-byte copy the producers now issue 3 (linear) / 4 (conv) instructions instead of ~9: the destination is one
+        // register + an immediate, the byte count (16 or 0 = zero fill) is a shift + mask of the per-row tap mask, and the
+        // source is one 64-bit add on a per-k-block base.  (The timeline showed the four producer warps -- one per scheduler,
+        // every dependent instruction fully exposed -- pacing the whole pipeline at ~710 cycles per k-block.)  A source
+        // address whose byte count is 0 is never dereferenced (cp.async zero-fill), so it needs no clamping.
+        if (fd.plain) {
+          const uint32_t kb = (kvalid && c < d.Cp) ? 16u : 0u;
+          const aldm_plane_t* ab = ahi + (kb ? c : 0);
+          const aldm_plane_t* abl = alo + (kb ? c : 0);
+          const uint32_t sa2 = sa + (uint32_t)rbase * 128u;
+          if (!(dbg & 1)) {
+#define ALDM_A_ROW(i)                                                                            \
+            {                                                                                      \
+              const uint32_t nb = tapmask[i] & kb;                                                 \
+              cp_async_16_off<(i) * 2048>(sa2, ab + rowoff[i], nb);                                \
+              if (AP == 2) cp_async_16_off<(i) * 2048 + C::A_BYTES>(sa2, abl + rowoff[i], nb);     \
             }
+            ALDM_A_ROW(0) ALDM_A_ROW(1) ALDM_A_ROW(2) ALDM_A_ROW(3) ALDM_A_ROW(4) ALDM_A_ROW(5) ALDM_A_ROW(6) ALDM_A_ROW(7)
+#undef ALDM_A_ROW
+          }
+        } else if (d.up == 0) {
+          const int tapoff = (d.dy[tp] * Ws + d.dx[tp]) * d.Cp + c;
+          const aldm_plane_t* ab = ahi + tapoff;
+          const aldm_plane_t* abl = alo + tapoff;
+          const int sh = kvalid ? tp : 27;                   // tapmask holds the validity bits pre-shifted by 4: (mask >> tp) & 16
+          const uint32_t sa2 = sa + (uint32_t)rbase * 128u;
+          if (!(dbg & 1)) {
+#define ALDM_A_ROW(i)                                                                            \
+            {                                                                                      \
+              const uint32_t nb = (tapmask[i] >> sh) & 16u;                                        \
+              cp_async_16_off<(i) * 2048>(sa2, ab + rowoff[i], nb);                                \
+              if (AP == 2) cp_async_16_off<(i) * 2048 + C::A_BYTES>(sa2, abl + rowoff[i], nb);     \
+            }
+            ALDM_A_ROW(0) ALDM_A_ROW(1) ALDM_A_ROW(2) ALDM_A_ROW(3) ALDM_A_ROW(4) ALDM_A_ROW(5) ALDM_A_ROW(6) ALDM_A_ROW(7)
+#undef ALDM_A_ROW
           }
         } else {      // nearest x2 upsample folded into the gather: source pixel = (ih >> 1, iw >> 1)
           const int dy = d.dy[tp], dx = d.dx[tp];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const bool ok = kvalid && ((tapmask[i] >> tp) & 1u);
+            const bool ok = kvalid && ((tapmask[i] >> (tp + 4)) & 1u);
             long long off = 0;
             if (ok) off = ((long long)(pbh[i] + ((ih0[i] + dy) >> 1)) * Ws + ((iw0[i] + dx) >> 1)) * d.Cp + c;
             const uint32_t dst = sa + (uint32_t)(rbase + 16 * i) * 128u;
@@ -517,7 +547,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     }
   } else if (warp == 4) {
     // ===================== B producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t cnt = 0;
       for (int id = blockIdx.x; id < total; id += gridDim.x) {
         int mt, nt, z, kb0, nkb;
@@ -537,8 +567,8 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     __syncwarp();
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN), idesc2 = umma_idesc_f16(128, 2 * BN);
       uint32_t cnt = 0, tl = 0;
       for (int id = blockIdx.x; id < total; id += gridDim.x, ++tl) {
         int mt, nt, z, kb0, nkb;
@@ -546,7 +576,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         const uint32_t acc = tl & 1;
         mbar_wait(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tmem_base + acc * BN;
+        const uint32_t tacc = tmem_base + acc * C::TMEM_COLS;
         for (int it = 0; it < nkb; ++it, ++cnt) {
           const int s = cnt % C::STAGES;
           mbar_wait(full_bar(s), (cnt / C::STAGES) & 1);
@@ -556,14 +586,20 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           const uint64_t da_hi = umma_desc_sw128(sa);
           const uint64_t da_lo = umma_desc_sw128(sa + C::A_BYTES);      // only used when AP == 2
           const uint64_t db_hi = umma_desc_sw128(sa + C::B_OFF);
-          const uint64_t db_lo = umma_desc_sw128(sa + C::B_OFF + C::B_BYTES);
+          const uint64_t db_lo = umma_desc_sw128(sa + C::B_OFF + C::B_BYTES);      // only used by the plain (not stacked) form
           if (!(dbg & 4)) {
+            // Measured (csrc/microbench.cu): a shared-memory-operand tcgen05.mma costs ~42 cycles + N / 2 -- the A fetch is
+            // not overlapped -- so one N = 256 instruction (169 cycles) is cheaper than two N = 128 ones (2 x 105).
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {            // 4 x K=16 (32 bytes) inside the 128B swizzle row
               const uint64_t o = (uint64_t)(ks * 2);
-              if (AP == 2) umma_f16(tacc, da_lo + o, db_hi + o, idesc, (it | ks) != 0);
-              umma_f16(tacc, da_hi + o, db_lo + o, idesc, AP == 2 ? 1u : (uint32_t)((it | ks) != 0));     // small terms first
-              umma_f16(tacc, da_hi + o, db_hi + o, idesc, 1);
+              if (C::ST) {
+                umma_f16(tacc, da_hi + o, db_hi + o, idesc2, (uint32_t)((it | ks) != 0));      // [A_hi W_hi^T | A_hi W_lo^T]
+                umma_f16(tacc, da_lo + o, db_hi + o, idesc, 1);                                // + A_lo W_hi^T into the first block
+              } else {
+                umma_f16(tacc, da_hi + o, db_lo + o, idesc, (uint32_t)((it | ks) != 0));       // small term first
+                umma_f16(tacc, da_hi + o, db_hi + o, idesc, 1);
+              }
             }
           }
           umma_commit(empty_bar(s));
@@ -611,12 +647,23 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           const int n = nt * BN + half * 32 + 64 * ch + (lane & 7) * 4;
           pb4[ch] = (d.bias && n < d.N) ? __ldg(reinterpret_cast<const float4*>(d.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (has_res && half * 32 < BN) co_load_res32(d, cr32, nt * BN + half * 32, d.N, lane, prv[0]);
+        // BOTH chunks' residuals are requested here, under the accumulator wait: issued after the first chunk was staged (the
+        // previous version) the loads queued behind the chunk's stores in the LSU -- 1,000-2,000 cycles from "staged" to
+        // "loads issued" in the timeline -- and the second chunk then waited for them.
+#pragma unroll
+        for (int ch = 0; ch < NRV; ++ch)
+          if (has_res && half * 32 + 64 * ch < BN) co_load_res32(d, cr32, nt * BN + half * 32 + 64 * ch, d.N, lane, prv[ch]);
       }
+      float gb_v = 0.f, gb_g = 0.f;       // GEGLU bias of this warp's value / gate chunk (lane = column)
+      if (EPI == EPI_GEGLU && d.bias && d.splitk == 1 && half * 32 < BN / 2) {
+        gb_v = __ldg(d.bias + nt * BN + half * 32 + lane);
+        gb_g = __ldg(d.bias + nt * BN + BN / 2 + half * 32 + lane);
+      }
+      if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8, 0);      // tile prologue (row decode, bias / residual prefetch) done
       mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
       if (warp == 6 && lane == 0) ALDM_TL(3, tl, 0);
       tc_fence_after();
-      const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(lb * 32) << 16);
+      const uint32_t trow = tmem_base + acc * C::TMEM_COLS + ((uint32_t)(lb * 32) << 16);
       if (dbg & 8) {
         // skip
       } else if (d.splitk > 1) {
@@ -626,8 +673,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN; c0 += 64) {
           uint32_t v[32];
-          tmem_ld32(trow + c0, v);
-          tmem_ld_wait();
+          acc_ld32<BN, C::ST>(trow + c0, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(v[i]);
           __syncwarp();
@@ -650,17 +696,26 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
         for (int c0 = half * 32; c0 < BN / 2; c0 += 64) {
           const int n0 = nt * (BN / 2) + c0;
           uint32_t vr[32], gr[32];
-          tmem_ld32(trow + c0, vr);
-          tmem_ld32(trow + BN / 2 + c0, gr);
-          tmem_ld_wait();
+          acc_ld32<BN, C::ST>(trow + c0, vr);
+          acc_ld32<BN, C::ST>(trow + BN / 2 + c0, gr);
+          if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 1, 0);
           float* v = reinterpret_cast<float*>(vr);
           float* g = reinterpret_cast<float*>(gr);
-          if (d.bias) { add_vec32(v, d.bias + nt * BN + c0); add_vec32(g, d.bias + nt * BN + BN / 2 + c0); }
+          // bias: fetched (one coalesced load per warp) BEFORE the accumulator wait, distributed by shuffles -- the broadcast
+          // float4 loads it replaces sat between the TMEM read and the GELU with a full L2 round trip exposed
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] += __shfl_sync(0xffffffffu, gb_v, i);
+            g[i] += __shfl_sync(0xffffffffu, gb_g, i);
+          }
 #pragma unroll      // full unroll: v/g must stay in registers (a partial unroll indexes them dynamically -> local memory)
-          for (int i = 0; i < 32; ++i) v[i] *= gelu_f(g[i]);
+          for (int i = 0; i < 32; i += 8) geglu_mul<8>(v + i, g + i);
+          if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 1, 1);
           if (d.out_mode == ALDM_OUT_PLANES) {      // the FF1 case: operand planes for FF2
             stage_rows(stg8, lane, v);
+            if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 2, 0);
             emit_rows<true>(d, cr, n0, n_out, stg8, lane, rv, false, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 2, 1);
           } else {
             epi_finish_coalesced(d, cr, n0, v, n_out, stg, lane, rv, false);
           }
@@ -672,12 +727,13 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           if (c0 < BN) {
             const int n0 = nt * BN + c0;
             uint32_t vr[32];
-            tmem_ld32(trow + c0, vr);
-            tmem_ld_wait();
+            acc_ld32<BN, C::ST>(trow + c0, vr);
+            if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 1 + 2 * ch, 0);
             stage_rows(stg8, lane, reinterpret_cast<const float*>(vr));
-            // the next chunk's residual is in flight while this one is written out
-            if (ch + 1 < NCH && has_res && c0 + 64 < BN) co_load_res32(d, cr32, n0 + 64, d.N, lane, prv[(ch + 1) % NRV]);
+            if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 1 + 2 * ch, 1);
+            if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 2 + 2 * ch, 0);
             emit_rows<EPI == EPI_PLN>(d, cr32, n0, d.N, stg8, lane, prv[ch % NRV], has_res, pb4[ch]);
+            if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 2 + 2 * ch, 1);
           }
         }
       } else if (EPI == EPI_FAST) {
@@ -690,8 +746,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           const bool pre = d.res != nullptr && !vpart;
           if (pre) co_load_res(d, cr, n0, d.N, lane, rv);
           uint32_t vr[32];
-          tmem_ld32(trow + c0, vr);
-          tmem_ld_wait();
+          acc_ld32<BN, C::ST>(trow + c0, vr);
           float* v = reinterpret_cast<float*>(vr);
           if (d.bias) add_vec32(v, d.bias + n0);
           if (d.rowvec) add_vec32(v, d.rowvec + (long long)r.b * d.ld_rowvec + n0);
@@ -721,15 +776,13 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           if (d.act == ALDM_ACT_GEGLU) {
             if (c0 >= BN / 2) break;
             uint32_t vr[32], gr[32];
-            tmem_ld32(trow + c0, vr);
-            tmem_ld32(trow + BN / 2 + c0, gr);
-            tmem_ld_wait();
+            acc_ld32<BN, C::ST>(trow + c0, vr);
+            acc_ld32<BN, C::ST>(trow + BN / 2 + c0, gr);
             epi_activate(d, r, nt * BN + c0, reinterpret_cast<float*>(vr), reinterpret_cast<float*>(gr));
             epi_finish(d, r, nt * (BN / 2) + c0, 32, reinterpret_cast<float*>(vr), d.N / 2);
           } else {
             uint32_t vr[32];
-            tmem_ld32(trow + c0, vr);
-            tmem_ld_wait();
+            acc_ld32<BN, C::ST>(trow + c0, vr);
             epi_activate(d, r, nt * BN + c0, reinterpret_cast<float*>(vr), nullptr);
             epi_finish(d, r, nt * BN + c0, 32, reinterpret_cast<float*>(vr), d.N);
           }
@@ -1018,6 +1071,9 @@ extern "C" int aldm_debug_timeline(long long* host_out, int32_t n) {
   using namespace aldm;
   ALDM_REQUIRE(host_out && n > 0 && n <= 4 * 256 * 2, ALDM_E_ARG, "debug_timeline: bad arguments");
   ALDM_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * n));
+  void* sym = nullptr;        // cleared after every read so that stamps of different cases never mix
+  ALDM_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_timeline));
+  ALDM_CHECK_CUDA(cudaMemset(sym, 0, sizeof(g_timeline)));
   return ALDM_OK;
 }
 

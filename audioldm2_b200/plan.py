@@ -240,10 +240,9 @@ class Planner:
         self.ops: List[dict] = []
         self.tag = 0
         self.marks: Dict[str, int] = {}
-        self.gn_scratch: Optional[Ref] = None
+        self._gn_scr: Dict[int, Ref] = {}       # GroupNorm scratch per batch size (its layout depends on B: csrc/prep.cu)
         self.splitk_ws: Optional[Ref] = None
         self.splitk_ws_bytes = 0
-        self._gn_scratch_bytes = 0
 
     # ---- weights -------------------------------------------------------------------------
     def vec(self, t: torch.Tensor) -> Ref:
@@ -335,11 +334,11 @@ class Planner:
 
     # ---- ops -----------------------------------------------------------------------------
     def _gn_scratch(self, B: int) -> Ref:
-        need = B * 64 * 32 * 2 * 8
-        if self.gn_scratch is None or need > self._gn_scratch_bytes:
-            self.gn_scratch = self.raw(need)
-            self._gn_scratch_bytes = need
-        return self.gn_scratch
+        # [B][64 blocks][32 groups][2] double partials | [B][32][2] float (mean, rstd) | [B] uint tickets (zero at start,
+        # self-resetting: the workspace is zero-initialised by engine.DeviceProgram and this buffer is never released)
+        if B not in self._gn_scr:
+            self._gn_scr[B] = self.raw(round_up(B * 64 * 32 * 2 * 8 + B * 32 * 2 * 4 + B * 4, 16))
+        return self._gn_scr[B]
 
     def prep(self, mode: int, src0: F32, src1: Optional[F32] = None, gamma: Optional[Ref] = None,
              beta: Optional[Ref] = None, eps: float = 0.0, slope: float = 0.0, B: int = 0, HW: int = 0,

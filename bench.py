@@ -483,7 +483,7 @@ def main():
             tcb = dict(error=repr(e))
     line = dict(metric=metric_name(a), value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=1000.0 * t_dev / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="bf16x3 (fp32-faithful split-bf16 tensor-core operands, fp32 accumulate)", data="synthetic",
+                dtype="f16x2 (split-fp16 tensor-core operands: weights hi + lo, activations hi + lo in the convolutions and one plane on the token side; fp32 accumulate, fp32 residual stream)", data="synthetic",
                 config=dict(workload=workload(a, cfg), lanes=lanes_used,
                             l2="no explicit flush: the UNet weights (1.39 GB for audioldm2-full) are re-streamed every DDIM step "
                                "(working set >> 126 MB L2)",

@@ -129,7 +129,8 @@ typedef struct aldm_prep_desc {
   const float* src0; const float* src1;
   const float* gamma; const float* beta;
   void* out_hi; void* out_lo;
-  double* scratch;           /* GN: [B*32*2] doubles, zeroed by the kernel sequence itself */
+  double* scratch;           /* GN: B*(64*32*2*8 + 32*2*4 + 4) bytes: per-block double partials, (mean, rstd) floats, ticket
+                                counters; must be ZERO before the first GroupNorm that uses it (the tickets reset themselves) */
   int32_t rows, c0, c1, Cp;
   int32_t B, HW, groups;
   int32_t mode;
@@ -320,6 +321,7 @@ size_t aldm_offsetof_gemm(int32_t field);     /* 0:B 1:ntaps 2:dy 3:N 4:ldo 5:ac
 const char* aldm_last_error(void);
 int aldm_device_check(int32_t device);
 int aldm_debug_timeline(long long* host_out, int32_t n);   /* profiling aid: per-stage clock64 stamps of CTA 0 (scripts/prof_ops.py --timeline) */        /* 0 if `device` is sm_100 and kernels can load */
+int aldm_debug_umma_rate(int32_t N, int32_t mode, int32_t reps, long long* host_out, int32_t n_out);   /* profiling aid: cycles for `reps` tcgen05.mma 128 x N x 16 on each of n_out SMs (scripts/umma_rate.py) */
 
 #ifdef __cplusplus
 }

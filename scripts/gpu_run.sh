@@ -47,16 +47,32 @@ while [ $# -gt 0 ]; do
     nettests)
       timeout 1500 python -m pytest tests/test_gpu_nets.py tests/test_gpu_zz_engine_abi.py -m gpu -q -s -p no:cacheprovider > gpurun_out/pytest_nets_$TAG.log 2>&1
       echo "== net tests rc=$?"; grep "rel L2\|passed\|failed\|FAILED\|Error" gpurun_out/pytest_nets_$TAG.log | tail -60 ;;
-    ncu-full)     # one --set full capture per dominant op shape (scripts/prof_ops.py cases) + the small HBM kernels
+    ncu-full)     # one --set full capture per dominant op shape (scripts/prof_ops.py cases) + the small HBM kernels; only the
+                  # raw-metric CSV comes back (gpurun_out is capped at 64 MiB: the .ncu-rep files stay on the box)
       for c in ${NCU_CASES:-lin_k1024_n256 lin_k256_n2048_geglu lin_k640_n640 conv_l2_256 attn_1024 ln_16384x256 gn_silu_l1}; do
         case $c in attn*) pat='attention_tc';; ln*) pat='ln_kernel';; gn*) pat='gn_apply_col';; *) pat='gemm_tc3';; esac
-        timeout 600 ncu --set full --clock-control none --import-source on -k regex:$pat -s 1 -c 1 -f -o gpurun_out/ncu_${TAG}_$c \
+        timeout 600 ncu --set full --clock-control none -k regex:$pat -s 1 -c 1 -f -o /tmp/ncu_${TAG}_$c \
           python scripts/prof_ops.py --reps 2 --only $c > gpurun_out/ncu_${TAG}_$c.log 2>&1
         echo "== ncu $c rc=$?"
+        ncu -i /tmp/ncu_${TAG}_$c.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_$c.csv 2>/dev/null
       done
-      timeout 600 ncu --set full --clock-control none -k regex:'ddim_step|stft_mel' -c 3 -f -o gpurun_out/ncu_${TAG}_small \
+      timeout 600 ncu --set full --clock-control none -k regex:'ddim_step|stft_mel' -c 3 -f -o /tmp/ncu_${TAG}_small \
         python scripts/prof_small.py 2 > gpurun_out/ncu_${TAG}_small.log 2>&1
-      echo "== ncu small rc=$?" ;;
+      echo "== ncu small rc=$?"
+      ncu -i /tmp/ncu_${TAG}_small.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_small.csv 2>/dev/null ;;
+    micro)        # tcgen05.mma issue rates + per-role timelines of the persistent GEMM (CTA 0)
+      timeout 300 python scripts/umma_rate.py > gpurun_out/umma_rate_$TAG.txt 2>&1; cat gpurun_out/umma_rate_$TAG.txt
+      timeout 300 python scripts/prof_ops.py --reps 20 --dbg 128 --only ${TL_CASES:-lin_k256_n256,lin_k1024_n256,lin_k256_n2048_geglu,conv_l2_256} > gpurun_out/timeline_$TAG.txt 2>&1
+      echo "== timeline"; grep -v "^  " gpurun_out/timeline_$TAG.txt ;;
+    step)         # ms per DDIM step of the default configuration
+      timeout 300 python scripts/step_time.py --lanes 1 --tag "$TAG" 2>gpurun_out/step_err.log | grep '^{' | tee gpurun_out/step_$TAG.json || tail -3 gpurun_out/step_err.log ;;
+    diag)         # what bounds the GEMM: dbg bits 1 skip A loads, 2 skip B loads, 4 skip MMA, 8 skip epilogue; 128 = timeline of CTA 0
+      : > gpurun_out/diag_$TAG.txt
+      for dbg in ${DIAG_BITS:-0 1 2 3 4 8 12 7 11 128}; do
+        echo "## dbg=$dbg" >> gpurun_out/diag_$TAG.txt
+        timeout 300 python scripts/prof_ops.py --reps 40 --dbg $dbg --only ${DIAG_CASES:-lin_k256_n256,lin_k1024_n256,lin_k256_n2048_geglu,lin_k640_n640,conv_l1_128,conv_l2_256} >> gpurun_out/diag_$TAG.txt 2>&1
+      done
+      echo "== diag"; grep -v "^  " gpurun_out/diag_$TAG.txt ;;
     ncu-list)
       timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
         --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 0 --ddim-steps 2 --no-graph --no-cpu-baseline \

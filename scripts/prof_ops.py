@@ -137,9 +137,12 @@ def main():
             for i in range(0, 40):
                 r = lambda x: (int(x) - t0) if int(x) > 0 else -1
                 print(f"  {i:4d} | {r(t[0, i, 0]):7d} {r(t[0, i, 1]):7d} | {r(t[1, i, 0]):7d} | {r(t[2, i, 0]):7d} {r(t[2, i, 1]):7d}")
-            print("  tile | epi: tfull_seen done")
+            print("  tile | epi: prologue_done tfull_seen | ch0: ld_done staged res_issued emitted | ch1: ld_done staged res_issued emitted | done"
+                  "   (GEGLU: ld_done gelu_done staged emitted)")
             for i in range(0, 4):
-                print(f"  {i:4d} | {r(t[3, i, 0]):7d} {r(t[3, i, 1]):7d}")
+                f = [r(t[3, 64 + i * 8 + k, ph]) for k in range(1, 5) for ph in (0, 1)]
+                print(f"  {i:4d} | {r(t[3, 64 + i * 8, 0]):7d} {r(t[3, i, 0]):7d} | " + " ".join(f"{x:7d}" for x in f[:4]) + " | " +
+                      " ".join(f"{x:7d}" for x in f[4:]) + f" | {r(t[3, i, 1]):7d}")
 
 
 if __name__ == "__main__":
