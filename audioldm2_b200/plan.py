@@ -240,7 +240,7 @@ class Planner:
         self.ops: List[dict] = []
         self.tag = 0
         self.marks: Dict[str, int] = {}
-        self._gn_scr: Dict[int, Ref] = {}       # GroupNorm scratch per batch size (its layout depends on B: csrc/prep.cu)
+        self._gn_scr: Dict[int, int] = {}       # GroupNorm scratch bytes per batch size (its layout depends on B: csrc/prep.cu)
         self.splitk_ws: Optional[Ref] = None
         self.splitk_ws_bytes = 0
 
@@ -334,11 +334,12 @@ class Planner:
 
     # ---- ops -----------------------------------------------------------------------------
     def _gn_scratch(self, B: int) -> Ref:
-        # [B][64 blocks][32 groups][2] double partials | [B][32][2] float (mean, rstd) | [B] uint tickets (zero at start,
-        # self-resetting: the workspace is zero-initialised by engine.DeviceProgram and this buffer is never released)
-        if B not in self._gn_scr:
-            self._gn_scr[B] = self.raw(round_up(B * 64 * 32 * 2 * 8 + B * 32 * 2 * 4 + B * 4, 16))
-        return self._gn_scr[B]
+        # [B][64 blocks][32 groups][2] double partials | [B][32][2] float (mean, rstd) | [B] uint tickets.  The tickets must be
+        # ZERO when a GroupNorm starts (they reset themselves): the buffer therefore cannot come from the pool's free list --
+        # a hole there belongs to buffers that other ops rewrite on every run -- and is placed above the high-water mark by
+        # finish(), like the split-K scratch (the workspace is zero-initialised once by engine.DeviceProgram).
+        self._gn_scr[B] = round_up(B * 64 * 32 * 2 * 8 + B * 32 * 2 * 4 + B * 4, ALIGN)
+        return "GNSCR%d" % B
 
     def prep(self, mode: int, src0: F32, src1: Optional[F32] = None, gamma: Optional[Ref] = None,
              beta: Optional[Ref] = None, eps: float = 0.0, slope: float = 0.0, B: int = 0, HW: int = 0,
@@ -419,6 +420,12 @@ class Planner:
             for o in self.ops:
                 if o.get("ws") == "SPLITK":
                     o["ws"] = ws
+        for B, nbytes in sorted(self._gn_scr.items()):
+            off = round_up(self.pool.peak, ALIGN)
+            self.pool.peak = off + nbytes
+            for o in self.ops:
+                if o.get("scratch") == "GNSCR%d" % B:
+                    o["scratch"] = Ref("ws", off)
         return Plan(self.ops, self.arena.build(), round_up(self.pool.peak, ALIGN), io, dict(self.marks), meta or {})
 
 

@@ -73,10 +73,9 @@ while [ $# -gt 0 ]; do
         timeout 300 python scripts/prof_ops.py --reps 40 --dbg $dbg --only ${DIAG_CASES:-lin_k256_n256,lin_k1024_n256,lin_k256_n2048_geglu,lin_k640_n640,conv_l1_128,conv_l2_256} >> gpurun_out/diag_$TAG.txt 2>&1
       done
       echo "== diag"; grep -v "^  " gpurun_out/diag_$TAG.txt ;;
-    ncu-list)
+    ncu-list)     # per-launch time + DRAM bytes of the UNet: 1 warm-up step (graph capture) + 1 measured DDIM step, graph kernel nodes
       timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
-        --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 0 --ddim-steps 2 --no-graph --no-cpu-baseline \
-        --no-torch-cuda-baseline --no-kernel-pass $BENCH_ARGS > gpurun_out/ncu_list_$TAG.log 2>&1
+        --csv --log-file gpurun_out/launches_$TAG.csv python scripts/step_time.py --steps 1 --warm 1 --reps 1 --tag ncu $NCU_LIST_ARGS > gpurun_out/ncu_list_$TAG.log 2>&1
       echo "== ncu-list rc=$?"; tail -2 gpurun_out/ncu_list_$TAG.log ;;
     *) echo "unknown job $job" ;;
   esac

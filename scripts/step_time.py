@@ -15,15 +15,17 @@ ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--model", default="audioldm2-full")
 ap.add_argument("--t5-len", type=int, default=32)
 ap.add_argument("--tag", default="")
+ap.add_argument("--warm", type=int, default=8, help="DDIM steps of the warm-up / graph-capture call")
+ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = arch.model_config(a.model)
 eng = model.build_synthetic(a.model, batch=a.batch, device=dev, t5_len=a.t5_len, lanes=a.lanes)
 cond, unc = synth.conditioning(cfg, a.batch, seed=77, t5_len=a.t5_len, device=dev)
-eng.generate_latent(cond, unc, ddim_steps=8)             # warm-up + graph capture
+eng.generate_latent(cond, unc, ddim_steps=a.warm)        # warm-up + graph capture
 torch.cuda.synchronize()
 best = None
-for rep in range(3):
+for rep in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.manual_seed(rep)
     e0.record(); eng.generate_latent(cond, unc, ddim_steps=a.steps); e1.record(); torch.cuda.synchronize()

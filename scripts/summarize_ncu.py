@@ -69,5 +69,47 @@ def rep(src, dst):
     print(open(dst).read()[:6000])
 
 
+EXACT = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+         "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+         "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
+         "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio",
+         "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio", "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio"]
+
+
+def csvs(dst, *srcs):
+    """raw-page CSVs exported on the GPU box (ncu -i X.ncu-rep --page raw --csv; the .ncu-rep files exceed the 64 MiB return cap)"""
+    with open(dst, "w") as f:
+        f.write("# ncu --set full --clock-control none, one launch per case (scripts/gpu_run.sh ncu-full; targets = scripts/prof_ops.py cases)\n\n")
+        for src in srcs:
+            rd = list(csv.reader(open(src, newline="")))
+            hdr_i = next((i for i, r in enumerate(rd) if r and r[0] == "ID"), None)
+            if hdr_i is None:
+                f.write(f"## {src}: no data\n\n")
+                continue
+            hdr, units, data = rd[hdr_i], rd[hdr_i + 1], rd[hdr_i + 2:]
+            for r in data:
+                if len(r) < len(hdr):
+                    continue
+                name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+                case = re.sub(r".*ncu_[a-z0-9]+_|\.csv$", "", src)
+                f.write(f"## {case}: `{name[:110]}`\n\n| metric | value | unit |\n|---|---|---|\n")
+                for k in EXACT:
+                    if k in hdr:
+                        i = hdr.index(k)
+                        f.write(f"| {k} | {r[i]} | {units[i]} |\n")
+                f.write("\n")
+    print(open(dst).read()[:5000])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "csv":
+        csvs(sys.argv[2], *sys.argv[3:])
+    else:
+        {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
