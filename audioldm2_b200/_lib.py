@@ -209,6 +209,7 @@ def lib() -> C.CDLL:
         "aldm_device_check": (i32, [i32]),
         "aldm_debug_timeline": (i32, [vp, i32]),
         "aldm_debug_umma_rate": (i32, [i32, i32, i32, vp, i32]),
+        "aldm_debug_store_rate": (i32, [i32, i32, i32, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the symbol is not exported
@@ -233,7 +234,7 @@ EXPORTED = ["aldm_gemm", "aldm_prep", "aldm_pack_b", "aldm_attention", "aldm_sof
             "aldm_engine_ddim_step", "aldm_engine_vae_decode", "aldm_engine_vocoder", "aldm_engine_vae_encode",
             "aldm_sizeof_engine_desc", "aldm_abi_version", "aldm_sizeof_op",
             "aldm_sizeof_gemm_desc", "aldm_offsetof_gemm", "aldm_last_error", "aldm_device_check", "aldm_debug_timeline",
-            "aldm_debug_umma_rate"]
+            "aldm_debug_umma_rate", "aldm_debug_store_rate"]
 
 
 def check(rc: int, what: str = ""):

@@ -125,52 +125,76 @@ __global__ void gn_apply_kernel(const __grid_constant__ aldm_prep_desc d, int nb
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, C % 4 == 0, C <= 1024
 // ---------------------------------------------------------------------------------------------
-__global__ void ln_kernel(const __grid_constant__ aldm_prep_desc d) {
-  pdl_wait();
+// NR rows per warp, all their loads issued before the first reduction: with one row per warp the kernel was a chain of
+// three dependent latencies (load -> mean -> variance -> store) per warp and 1.7 waves of blocks for 16,384 rows.
+template <int NQ, int NR>       // NQ float4 per lane (C <= 128 * NQ)
+__global__ void __launch_bounds__(256) ln_kernel(const __grid_constant__ aldm_prep_desc d) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= d.rows) return;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * NR;
   const int C = d.c0, Q = C >> 2;
-  float4 v[8];
-  float s = 0.f;
+  pdl_wait();
+  if (row0 >= d.rows) return;
+  float4 v[NR][NQ];
+  float s[NR];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int q = lane + 32 * i;
-    if (q < Q) {
-      v[i] = *reinterpret_cast<const float4*>(d.src0 + row * C + q * 4);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int r = 0; r < NR; ++r) {
+    s[r] = 0.f;
+    const bool rv = row0 + r < d.rows;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const int q = lane + 32 * i;
+      v[r][i] = (rv && q < Q) ? *reinterpret_cast<const float4*>(d.src0 + (row0 + r) * C + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  pdl_launch();      // late trigger: the row is in registers; see common.cuh on why not at kernel entry
-  float s2 = 0.f;
+  for (int r = 0; r < NR; ++r) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int q = lane + 32 * i;
-    if (q < Q) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-      s2 += (a * a + b * b) + (c * c + e * e);
+    for (int i = 0; i < NQ; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  }
+  pdl_launch();      // late trigger: the rows are in registers; see common.cuh on why not at kernel entry
+  float mean[NR], s2[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    mean[r] = s[r] / C;
+    s2[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      if (lane + 32 * i < Q) {
+        const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], e = v[r][i].w - mean[r];
+        s2[r] += (a * a + b * b) + (c * c + e * e);
+      }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  const float rstd = rsqrtf(s2 / C + d.eps);
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+  }
   aldm_plane_t* hi = reinterpret_cast<aldm_plane_t*>(d.out_hi);
   aldm_plane_t* lo = reinterpret_cast<aldm_plane_t*>(d.out_lo);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int q = lane + 32 * i;
     if (q < Q) {
-      const float4 g = *reinterpret_cast<const float4*>(d.gamma + q * 4);
-      const float4 be = *reinterpret_cast<const float4*>(d.beta + q * 4);
-      float y[4];
-      y[0] = (v[i].x - mean) * rstd * g.x + be.x;
-      y[1] = (v[i].y - mean) * rstd * g.y + be.y;
-      y[2] = (v[i].z - mean) * rstd * g.z + be.z;
-      y[3] = (v[i].w - mean) * rstd * g.w + be.w;
-      store_planes4(hi, lo, row * d.Cp + q * 4, y);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + q * 4));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(d.beta + q * 4));
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (row0 + r < d.rows) {
+          const float rstd = rsqrtf(s2[r] / C + d.eps);
+          float y[4];
+          y[0] = (v[r][i].x - mean[r]) * rstd * g.x + be.x;
+          y[1] = (v[r][i].y - mean[r]) * rstd * g.y + be.y;
+          y[2] = (v[r][i].z - mean[r]) * rstd * g.z + be.z;
+          y[3] = (v[r][i].w - mean[r]) * rstd * g.w + be.w;
+          store_planes4(hi, lo, (row0 + r) * d.Cp + q * 4, y);
+        }
+      }
     }
   }
 }
@@ -247,7 +271,7 @@ __device__ __forceinline__ unsigned* gn_ticket_ptr(const aldm_prep_desc& d) {
   return reinterpret_cast<unsigned*>(gn_stats_ptr(d) + (size_t)d.B * 32 * 2);
 }
 
-__global__ void __launch_bounds__(256) gn_stats_col_kernel(const __grid_constant__ aldm_prep_desc d, int nblk) {
+__global__ void __launch_bounds__(256) gn_stats_col_kernel(const __grid_constant__ aldm_prep_desc d, int nblk, int finalize) {
   __shared__ float s_a[GN_MAX_C / 4], s_a2[GN_MAX_C / 4];      // [slot][q], RS * Q <= max(256, Q)
   __shared__ double s_red[8][32][2];
   __shared__ int s_last;
@@ -293,8 +317,9 @@ __global__ void __launch_bounds__(256) gn_stats_col_kernel(const __grid_constant
     double* p = d.scratch + (((long long)b * nblk + blk) * d.groups + g) * 2;
     p[0] = s;
     p[1] = s2;
-    __threadfence();
+    if (finalize) __threadfence();
   }
+  if (!finalize) return;      // few blocks per batch row: the apply kernel reduces the partials itself (no ticket round trip)
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(gn_ticket_ptr(d) + b, 1u);
@@ -330,7 +355,9 @@ __global__ void __launch_bounds__(256) gn_stats_col_kernel(const __grid_constant
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_col_kernel(const __grid_constant__ aldm_prep_desc d) {
+__global__ void __launch_bounds__(256) gn_apply_col_kernel(const __grid_constant__ aldm_prep_desc d, int nblk_partials) {
+  __shared__ double s_red[8][32][2];
+  __shared__ float s_st[64];
   const int b = blockIdx.y;
   const int C = d.c0 + d.c1, cpg = C / d.groups;
   const GnGeom gg = gn_geom(C);
@@ -341,13 +368,39 @@ __global__ void __launch_bounds__(256) gn_apply_col_kernel(const __grid_constant
   aldm_plane_t* lo = reinterpret_cast<aldm_plane_t*>(d.out_lo);
   const bool act = d.mode == ALDM_PREP_GN_SILU;
   pdl_wait();
-  const float* st = gn_stats_ptr(d) + (long long)b * 64;
+  if (nblk_partials > 0) {
+    // small tensors: fixed-order reduction of the (<= 8) per-block partials, all threads in parallel
+    const int g = threadIdx.x & 31, ks = threadIdx.x >> 5, nsl = blockDim.x >> 5;
+    double s = 0.0, s2 = 0.0;
+    for (int k = ks; k < nblk_partials; k += nsl) {
+      const double* p = d.scratch + (((long long)b * nblk_partials + k) * d.groups + g) * 2;
+      s += p[0];
+      s2 += p[1];
+    }
+    s_red[ks][g][0] = s;
+    s_red[ks][g][1] = s2;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      s = 0.0; s2 = 0.0;
+      for (int k = 0; k < nsl; ++k) { s += s_red[k][g][0]; s2 += s_red[k][g][1]; }
+      const double n = (double)d.HW * cpg;
+      const double mean = s / n;
+      double var = s2 / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_st[2 * g] = (float)mean;
+      s_st[2 * g + 1] = (float)(1.0 / sqrt(var + (double)d.eps));
+    }
+  } else if (threadIdx.x < 64) {
+    s_st[threadIdx.x] = __ldcg(gn_stats_ptr(d) + (long long)b * 64 + threadIdx.x);
+  }
+  __syncthreads();
+  const float* st = s_st;
   const long long rb = (long long)b * d.HW;
   for (int q = q0; q < gg.Q; q += gg.QW) {
     const int g = (q * 4) / cpg;
     const float4 ga = __ldg(reinterpret_cast<const float4*>(d.gamma + q * 4));
     const float4 be = __ldg(reinterpret_cast<const float4*>(d.beta + q * 4));
-    const float mu = __ldcg(st + g * 2), rs = __ldcg(st + g * 2 + 1);
+    const float mu = st[g * 2], rs = st[g * 2 + 1];
     const float sc[4] = {rs * ga.x, rs * ga.y, rs * ga.z, rs * ga.w};
     const float sh[4] = {be.x - mu * sc[0], be.y - mu * sc[1], be.z - mu * sc[2], be.w - mu * sc[3]};
     auto emit = [&](long long row, const float4& v) {
@@ -394,15 +447,16 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
       const int thr = gg.QW * gg.RS;                 // multiple of 32 (Q is a multiple of 32 here), <= 256
       const int unit = 4 * gg.RS * cdiv(gg.Q, gg.QW);   // rows that give one thread four loads per column pass
       int nblk = cdiv(4 * 148, d.B);
-      if (nblk > cdiv(d.HW, unit)) nblk = cdiv(d.HW, unit);
+      if (nblk > cdiv(d.HW, 2 * unit)) nblk = cdiv(d.HW, 2 * unit);
       if (nblk > GN_MAX_BLOCKS) nblk = GN_MAX_BLOCKS;
       if (nblk < 1) nblk = 1;
-      ALDM_CHECK_CUDA(launch_pdl(gn_stats_col_kernel, dim3(nblk, d.B), dim3(thr), 0, st, d, nblk));
+      const int finalize = nblk > 8 ? 1 : 0;       // last-block finalisation only pays when the apply blocks would re-reduce many partials
+      ALDM_CHECK_CUDA(launch_pdl(gn_stats_col_kernel, dim3(nblk, d.B), dim3(thr), 0, st, d, nblk, finalize));
       ALDM_CHECK_CUDA(cudaGetLastError());
       int nap = cdiv(8 * 148, d.B);
       if (nap > cdiv(d.HW, unit)) nap = cdiv(d.HW, unit);
       if (nap < 1) nap = 1;
-      ALDM_CHECK_CUDA(launch_pdl(gn_apply_col_kernel, dim3(nap, d.B), dim3(thr), 0, st, d));
+      ALDM_CHECK_CUDA(launch_pdl(gn_apply_col_kernel, dim3(nap, d.B), dim3(thr), 0, st, d, finalize ? 0 : nblk));
       ALDM_CHECK_CUDA(cudaGetLastError());
     } else {
       int nblk = cdiv(d.HW, 32);
@@ -417,7 +471,10 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
   } else if (d.mode == ALDM_PREP_LN) {
     ALDM_REQUIRE(d.gamma && d.beta, ALDM_E_ARG, "prep LN: null gamma/beta");
     ALDM_REQUIRE(d.c1 == 0 && C % 4 == 0 && C <= 1024 && d.Cp == C, ALDM_E_UNSUPPORTED, "prep LN: C=%d", C);
-    ALDM_CHECK_CUDA(launch_pdl(ln_kernel, dim3(cdiv(d.rows, 8)), dim3(256), 0, st, d));
+    // one row per warp (NR = 2, two rows in flight per warp, measured SLOWER: 9.8 vs 8.2 us at 16384 x 256); float4 per lane sized to C
+    const dim3 grid(cdiv(d.rows, 8));
+    ALDM_CHECK_CUDA(C <= 256 ? launch_pdl(ln_kernel<2, 1>, grid, dim3(256), 0, st, d)
+                             : (C <= 512 ? launch_pdl(ln_kernel<4, 1>, grid, dim3(256), 0, st, d) : launch_pdl(ln_kernel<8, 1>, grid, dim3(256), 0, st, d)));
     ALDM_CHECK_CUDA(cudaGetLastError());
   } else {
     ALDM_REQUIRE(d.mode == ALDM_PREP_COPY || d.mode == ALDM_PREP_SILU || d.mode == ALDM_PREP_LRELU, ALDM_E_ARG,

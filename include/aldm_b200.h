@@ -322,6 +322,7 @@ const char* aldm_last_error(void);
 int aldm_device_check(int32_t device);
 int aldm_debug_timeline(long long* host_out, int32_t n);   /* profiling aid: per-stage clock64 stamps of CTA 0 (scripts/prof_ops.py --timeline) */        /* 0 if `device` is sm_100 and kernels can load */
 int aldm_debug_umma_rate(int32_t N, int32_t mode, int32_t reps, long long* host_out, int32_t n_out);   /* profiling aid: cycles for `reps` tcgen05.mma 128 x N x 16 on each of n_out SMs (scripts/umma_rate.py) */
+int aldm_debug_store_rate(int32_t n_cta, int32_t iters, int32_t mode, long long region_bytes, long long* host_out);   /* profiling aid: SM -> L2 store throughput, STG.128 (0) vs TMA bulk store (1) (scripts/store_rate.py) */
 
 #ifdef __cplusplus
 }
