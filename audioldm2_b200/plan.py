@@ -267,11 +267,21 @@ class Planner:
              bn: Optional[int] = None, m_rows: Optional[int] = None) -> WMat:
         N, K = wm.shape
         assert K == ntaps * cp
-        # Measured (profiles/r01_unet_ops_v4_eager.csv vs v5): narrower tiles for small-M GEMMs are SLOWER
-        # (more CTAs re-read the same activation rows, MMA N=32/64 is less efficient), so the widest tile
-        # that divides N is always used; m_rows is kept for future tuning.
+        # Measured (profiles/r01_unet_ops_v4_eager.csv vs v5, and again in round 2: ALDM_NARROW=64 / 32 -> 16.3 / 17.5 ms per DDIM
+        # step against 16.1): narrower tiles as a general rule for small-M GEMMs are SLOWER (a second wave at the 256-pixel level,
+        # twice the weight traffic and no split-K for the long-K convolutions).  One case is different: a SHORT-K GEMM whose
+        # 128-wide tiles fill at most half the SMs (the 64-pixel level: 1024 x 640 x 640 = 40 tiles on 148 SMs) is a pure latency
+        # chain load -> MMA -> 64 KB of stores per CTA; halving the tile width halves the store phase (32 B/clk/SM store port,
+        # profiles/r02_store_port_rate.txt) and cuts the MMA time by 30 % (N = 64: 74 cycles per instruction against 105 for
+        # N = 128) while the tiles still fit one wave.  ALDM_HALF_TILES=0 switches it off (A/B).
         narrow = int(os.environ.get("ALDM_NARROW", "0"))       # experiment switch: smallest N tile the heuristic may pick
+        explicit = bn is not None
         bn = bn or self.bn_for_rows(N, m_rows if narrow else None, geglu, min_bn=narrow or 32)
+        if (not explicit and not narrow and m_rows and bn == 128 and N % 64 == 0 and os.environ.get("ALDM_HALF_TILES", "1") != "0"
+                and math.ceil(K / 64) < 24 and not geglu):
+            tiles = math.ceil(m_rows / 128) * math.ceil(N / 128)
+            if tiles * 2 <= self.n_sm:
+                bn = 64
         if geglu:
             order = packing.geglu_row_order(N // 2, bn)
             wm = wm[order]
