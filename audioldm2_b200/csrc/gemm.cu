@@ -280,6 +280,32 @@ __device__ __forceinline__ void emit_rows(const aldm_gemm_desc& d, const CR& cr,
   __syncwarp();
 }
 
+// ---- full-line finish for single-plane fp16 outputs (EPI_PLN, EPI_GEGLU -> planes) ------------------------
+// A warp's 32 x 32 chunk is only 64 bytes per row in fp16: stored by itself it is a stream of half-line transactions, and the
+// SM's store port moves one transaction per clock whatever its size (32 B/clk for full lines: profiles/r02_store_port_rate.txt;
+// the GEGLU epilogue spent 2,500 of its 5,100 cycles per tile storing 16 KB).  The two warps that own the same TMEM lane quarter
+// (chunk parity 0 / 1: columns [0,32) and [32,64) of one 64-column group) therefore assemble the 32 x 64 fp16 block in a shared
+// tile (rows of 128 bytes, 16-byte chunks XOR-swizzled by the row), meet at a 64-thread named barrier, and each stores 16
+// complete 128-byte rows: 4 STG.128 per warp instead of 8 STG.64.  Two tiles alternate, so one barrier per block suffices.
+template <typename CR>
+__device__ __forceinline__ void emit_pair_hi(const aldm_gemm_desc& d, const CR& cr, int n_pair0, uint8_t* tile, int lane, int half,
+                                             int bar_id, const float* v) {
+  uint8_t* wr = tile + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(wr + (((half * 4 + j) ^ sw) << 4)) = pack8_hi(v + 8 * j);
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  const int rs = lane >> 3, c8 = lane & 7;
+  aldm_plane_t* out = reinterpret_cast<aldm_plane_t*>(d.out_hi);
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = half * 16 + it * 4 + rs;
+    const uint4 x = *reinterpret_cast<const uint4*>(tile + rr * 128 + ((c8 ^ (rr & 7)) << 4));
+    const auto orow = half ? cr.orow[4 + it] : cr.orow[it];
+    if ((cr.vmask >> rr) & 1u) *reinterpret_cast<uint4*>(out + (orow * d.ldo + n_pair0 + c8 * 8)) = x;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------
@@ -616,7 +642,7 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
     const int half = (warp - 6) >> 2;
     const int trow_in_tile = lb * 32 + lane;
     float* stg = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - raw)) + (warp - 6) * (32 * 33);
-    uint32_t tl = 0;
+    uint32_t tl = 0, pair_cnt = 0;
     for (int id = blockIdx.x; id < total; id += gridDim.x, ++tl) {
       int mt, nt, z, kb0, nkb;
       tile_coords(id, mt, nt, z, kb0, nkb);
@@ -653,6 +679,21 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
 #pragma unroll
         for (int ch = 0; ch < NRV; ++ch)
           if (has_res && half * 32 + 64 * ch < BN) co_load_res32(d, cr32, nt * BN + half * 32 + 64 * ch, d.N, lane, prv[ch]);
+      }
+      // full-line pair mode (emit_pair_hi): single fp16 plane out, no residual, whole 64-column groups
+      const bool pair_pln = EPI == EPI_PLN && BN >= 64 && d.out_lo == nullptr && d.res == nullptr && d.splitk == 1 && d.N % 64 == 0 &&
+                            d.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out_hi) & 15u) == 0;
+      const bool pair_geglu = EPI == EPI_GEGLU && BN == 128 && d.out_mode == ALDM_OUT_PLANES && d.out_lo == nullptr && d.splitk == 1 &&
+                              (d.N / 2) % 64 == 0 && d.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out_hi) & 15u) == 0;
+      const bool pair_qk = EPI == EPI_FAST && BN >= 64 && d.out_mode == ALDM_OUT_QKV && d.out_lo == nullptr && d.res == nullptr &&
+                           d.splitk == 1 && d.n_split % 64 == 0 && d.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out_hi) & 15u) == 0;
+      uint8_t* pair_tiles = reinterpret_cast<uint8_t*>(smem_raw + (bar_base + 256 - raw)) + ((warp - 6) & 3) * (32 * 33 * 4);
+      const int pair_bar = 1 + ((warp - 6) & 3);
+      float pln_b[NCH > 0 ? NCH : 1];      // bias of this warp's columns (lane = column), distributed by shuffles in pair mode
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int n = nt * BN + half * 32 + 64 * ch + lane;
+        pln_b[ch] = (pair_pln && d.bias && n < d.N) ? __ldg(d.bias + n) : 0.f;
       }
       float gb_v = 0.f, gb_g = 0.f;       // GEGLU bias of this warp's value / gate chunk (lane = column)
       if (EPI == EPI_GEGLU && d.bias && d.splitk == 1 && half * 32 < BN / 2) {
@@ -711,7 +752,10 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
 #pragma unroll      // full unroll: v/g must stay in registers (a partial unroll indexes them dynamically -> local memory)
           for (int i = 0; i < 32; i += 8) geglu_mul<8>(v + i, g + i);
           if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 1, 1);
-          if (d.out_mode == ALDM_OUT_PLANES) {      // the FF1 case: operand planes for FF2
+          if (pair_geglu) {                         // the FF1 case: one fp16 plane for FF2, stored as full lines by the warp pair
+            emit_pair_hi(d, cr, nt * (BN / 2), pair_tiles + ((pair_cnt++ & 1u) ? 4 * (32 * 33 * 4) : 0), lane, half, pair_bar, v);
+            if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 2, 1);
+          } else if (d.out_mode == ALDM_OUT_PLANES) {
             stage_rows(stg8, lane, v);
             if (warp == 6 && lane == 0) ALDM_TL(3, 64 + tl * 8 + 2, 0);
             emit_rows<true>(d, cr, n0, n_out, stg8, lane, rv, false, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -719,6 +763,19 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           } else {
             epi_finish_coalesced(d, cr, n0, v, n_out, stg, lane, rv, false);
           }
+        }
+      } else if (kCompact && pair_pln) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c0 = half * 32 + 64 * ch;      // < BN: BN >= 64 in pair mode
+          uint32_t vr[32];
+          acc_ld32<BN, C::ST>(trow + c0, vr);
+          float* v = reinterpret_cast<float*>(vr);
+          if (d.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, pln_b[ch], i);
+          }
+          emit_pair_hi(d, cr32, nt * BN + 64 * ch, pair_tiles + ((pair_cnt++ & 1u) ? 4 * (32 * 33 * 4) : 0), lane, half, pair_bar, v);
         }
       } else if (kCompact) {
 #pragma unroll
@@ -750,7 +807,10 @@ __global__ void __launch_bounds__(448, 1) gemm_tc3_kernel(const __grid_constant_
           float* v = reinterpret_cast<float*>(vr);
           if (d.bias) add_vec32(v, d.bias + n0);
           if (d.rowvec) add_vec32(v, d.rowvec + (long long)r.b * d.ld_rowvec + n0);
-          if (!vpart) {
+          if (!vpart && pair_qk) {
+            // Q | K planes (one fp16 plane, 64 bytes per row and chunk): full-line stores by the warp pair (emit_pair_hi)
+            emit_pair_hi(d, cr, nt * BN + (c0 & ~63), pair_tiles + ((pair_cnt++ & 1u) ? 4 * (32 * 33 * 4) : 0), lane, half, pair_bar, v);
+          } else if (!vpart) {
             epi_finish_coalesced(d, cr, n0, v, d.N, stg, lane, rv, pre);
           } else if (r.valid) {
             // V projection: transposed planes, lane == token -> consecutive lanes write consecutive bf16

@@ -613,12 +613,18 @@ def build_unet(sd: Dict[str, torch.Tensor], cfg: dict, latent: Tuple[int, int, i
             P.gemm(p, P.wmat(wm, sd[b + ".ff.net.0.proj.bias"], taps, cp, geglu=True, m_rows=h.rows), B=1, H=h.rows, out_planes=g,
                    act=_lib.ACT_GEGLU)
             P.free(p)
-            h2 = P.f32(h.rows, Cc)
             last = d == l.depth - 1
-            hp = P.planes(h.rows, Cc) if last else None      # proj_out's operand, written by the same epilogue
-            P.gemm(g, P.conv_w(sd, b + ".ff.net.2", m_rows=h.rows), B=1, H=h.rows, out=h2, res=h, also_planes=hp)
-            P.free(g, h); h = h2
-        p = hp; P.free(h)
+            if last:
+                # the last block's output is only ever read as proj_out's operand: write the planes alone (the fp32 copy the
+                # dual-output form also stored was dead -- 64 KB per tile through a 32 B/clk store port)
+                hp = P.planes(h.rows, Cc)
+                P.gemm(g, P.conv_w(sd, b + ".ff.net.2", m_rows=h.rows), B=1, H=h.rows, out_planes=hp, res=h)
+                P.free(g, h); h = None
+            else:
+                h2 = P.f32(h.rows, Cc)
+                P.gemm(g, P.conv_w(sd, b + ".ff.net.2", m_rows=h.rows), B=1, H=h.rows, out=h2, res=h)
+                P.free(g, h); h = h2
+        p = hp
         out = P.f32(x.rows, Cc)
         P.gemm(p, P.conv_w(sd, n + ".proj_out", m_rows=x.rows), B=Bt, H=H, W=W, out=out, res=x)
         P.free(p)

@@ -21,6 +21,7 @@ from audioldm2_b200.plan import F32, Planner  # noqa: E402
 CASES = {
     # name: (kind, params)
     "lin_k256_n256": ("gemm", dict(B=1, H=16384, W=1, Cin=256, N=256, taps=((0, 0),), res=True)),
+    "lin_k256_n256_pln": ("gemm", dict(B=1, H=16384, W=1, Cin=256, N=256, taps=((0, 0),), pln=True)),
     "lin_k256_n2048_geglu": ("gemm", dict(B=1, H=16384, W=1, Cin=256, N=2048, taps=((0, 0),), geglu=True)),
     "lin_k256_n768_qkv": ("gemm", dict(B=1, H=16384, W=1, Cin=256, N=768, taps=((0, 0),), qkv=1024)),
     "lin_k1024_n256": ("gemm", dict(B=1, H=16384, W=1, Cin=1024, N=256, taps=((0, 0),), res=True)),
@@ -60,6 +61,9 @@ def build(name, impl):
         if p.get("geglu"):
             w = P.wmat(wm, torch.zeros(N), len(taps), Cin, geglu=True)
             P.gemm(a, w, out_planes=P.planes(M, N // 2, tok), act=_lib.ACT_GEGLU, **kw)
+        elif p.get("pln"):
+            w = P.wmat(wm, torch.zeros(N), len(taps), Cin)
+            P.gemm(a, w, out_planes=P.planes(M, N, tok), **kw)
         elif p.get("qkv"):
             Cc = N // 3
             w = P.wmat(wm, None, len(taps), Cin, bn=P.bn_for_split(N, 2 * Cc))
