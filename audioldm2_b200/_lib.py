@@ -140,8 +140,6 @@ def build(verbose: bool = False, force: bool = False) -> str:
         o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
         objs.append(o)
         cmd = ["nvcc"] + [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-c", s, "-o", o]
-        if os.environ.get("ALDM_BUILD_EXPERIMENTAL") == "1":     # compiled-out experiments (TMA A path); see scripts/gpu_experiments.sh
-            cmd.insert(1, "-DALDM_EXPERIMENTAL_TMA")
         if verbose:
             print(" ".join(cmd))
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

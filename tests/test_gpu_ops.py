@@ -97,6 +97,41 @@ def test_groupnorm_fast_path():
         assert rel_l2(read_gpu_planes(prog, o), em.read_planes(o.hi, o.lo, o.rows, o.Cp)) < 2e-5
 
 
+@pytest.mark.parametrize("B,HW,C", [(2, 4096, 128), (16, 64, 640), (3, 1000, 256), (2, 300, 1280)])
+def test_groupnorm_large_and_repeated(B, HW, C):
+    """(slot, q) GroupNorm kernels: many blocks per batch row (statistics published by the last block through the self-resetting
+    ticket) and few (the apply kernel reduces the partials); a second run must see the tickets back at zero."""
+    g = torch.Generator().manual_seed(5)
+    P = Planner(keep_plain=True)
+    a = F32(P.raw(B * HW * C * 4), B * HW, C)
+    junk = P.raw(1 << 20); P.free(junk)          # a freed hole: the GroupNorm scratch must not land in reusable pool space
+    gam = P.vec(1 + 0.1 * torch.randn(C, generator=g)); bet = P.vec(0.1 * torch.randn(C, generator=g))
+    o1 = P.prep(_lib.PREP_GN_SILU, a, None, gam, bet, eps=1e-5, B=B, HW=HW)
+    o2 = P.prep(_lib.PREP_GN, a, None, gam, bet, eps=1e-6, B=B, HW=HW, n=1)
+    pl = P.finish(dict(a=("f32", a.ref, (a.rows, a.C))))
+    x = torch.randn(a.rows, a.C, generator=g) * 3 + 1.5
+    em, prog = run_both(pl, dict(a=x))
+    want = [em.read_planes(o.hi, o.lo, o.rows, o.Cp) for o in (o1, o2)]
+    for rep in range(3):
+        if rep:
+            prog.run("all"); torch.cuda.synchronize()
+        for o, w in zip((o1, o2), want):
+            assert rel_l2(read_gpu_planes(prog, o), w) < (2e-5 if o.lo is not None else 3e-4), (rep, B, HW, C)
+
+
+@pytest.mark.parametrize("C", [96, 256, 384, 640, 1024])
+def test_layernorm_widths(C):
+    """ln_kernel<NQ>: float4 per lane sized to C (2 / 4 / 8)."""
+    g = torch.Generator().manual_seed(C)
+    P = Planner(keep_plain=True)
+    rows = 333
+    a = F32(P.raw(rows * C * 4), rows, C)
+    gam = P.vec(1 + 0.1 * torch.randn(C, generator=g)); bet = P.vec(0.1 * torch.randn(C, generator=g))
+    o = P.prep(_lib.PREP_LN, a, None, gam, bet, eps=1e-5, n=1)
+    em, prog = run_both(P.finish(dict(a=("f32", a.ref, (rows, C)))), dict(a=torch.randn(rows, C, generator=g) * 2 + 0.7))
+    assert rel_l2(read_gpu_planes(prog, o), em.read_planes(o.hi, o.lo, o.rows, o.Cp)) < 3e-4
+
+
 @pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("mode", ["copy", "silu", "lrelu", "gn", "gn_silu", "ln", "nchw", "cat", "pad"])
 def test_prep_modes(mode, planes):
@@ -187,6 +222,13 @@ GEMM_CASES = {
     "a1_geglu_p1": dict(B=1, H=200, W=1, Cin=256, N=512, taps=((0, 0),), geglu=True, act=_lib.ACT_GEGLU, out_kind="planes",
                         a_planes=1, out_planes_n=1),
     "a1_planes_p1": dict(B=1, H=260, W=1, Cin=128, N=256, taps=((0, 0),), out_kind="planes", a_planes=1, out_planes_n=1),
+    # full-line pair stores with 64-wide tiles, without bias, with a residual (falls back to the per-warp stores) and two-plane output
+    "a1_planes_p1_n192": dict(B=1, H=700, W=1, Cin=128, N=192, taps=((0, 0),), out_kind="planes", a_planes=1, out_planes_n=1),
+    "a1_planes_p1_nobias": dict(B=1, H=515, W=1, Cin=64, N=128, taps=((0, 0),), out_kind="planes", a_planes=1, out_planes_n=1, bias=False),
+    "a1_planes_p2_res": dict(B=1, H=400, W=1, Cin=256, N=256, taps=((0, 0),), out_kind="planes", a_planes=1, res=True),
+    "a1_planes_p1_res": dict(B=1, H=400, W=1, Cin=256, N=256, taps=((0, 0),), out_kind="planes", a_planes=1, out_planes_n=1, res=True),
+    "a1_geglu_p1_wide": dict(B=1, H=1000, W=1, Cin=128, N=1024, taps=((0, 0),), geglu=True, act=_lib.ACT_GEGLU, out_kind="planes",
+                             a_planes=1, out_planes_n=1),
     "a1_dual_p2": dict(B=1, H=300, W=1, Cin=1024, N=256, taps=((0, 0),), res=True, dual=True, a_planes=1),
     "a1_conv3x3": dict(B=2, H=20, W=6, Cin=24, N=128, taps=plan.TAPS_3x3, rowvec=True, res=True, a_planes=1),
     "a1_deepK_splitk": dict(B=2, H=8, W=2, Cin=640, N=640, taps=plan.TAPS_3x3, res=True, a_planes=1),
@@ -280,11 +322,13 @@ def test_attention(case, impl):
 
 @pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("impl", ["simt", "tc"])
-def test_gemm_qkv_output(impl, planes):
-    """ALDM_OUT_QKV: Q|K columns as planes, V columns as transposed planes (keys contiguous, pad zeroed)."""
+@pytest.mark.parametrize("Cc", [64, 128])
+def test_gemm_qkv_output(impl, planes, Cc):
+    """ALDM_OUT_QKV: Q|K columns as planes (full-line pair stores when single-plane), V columns as transposed planes (keys contiguous,
+    pad zeroed); 64- and 128-wide tiles."""
     g = torch.Generator().manual_seed(11)
     P = Planner(impl=impl, keep_plain=True)
-    Bt, HW, Cc = 3, 37, 64
+    Bt, HW = 3, 37
     rows = Bt * HW
     src = F32(P.raw(rows * Cc * 4), rows, Cc)
     a = P.prep(_lib.PREP_COPY, src, n=planes)

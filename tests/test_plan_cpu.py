@@ -8,7 +8,7 @@ token-side activations of the UNet -- so first-stage networks agree with the fp3
 import pytest
 import torch
 
-from audioldm2_b200 import arch, packing, plan, synth
+from audioldm2_b200 import _lib, arch, packing, plan, synth
 from tests.conftest import rel_l2
 from tests.emulator import Emulator
 from tests.golden import cases
@@ -162,3 +162,34 @@ def test_pool_allocator_reuses_and_never_overlaps():
     for (o1, n1), (o2, n2) in zip(live, live[1:]):
         assert o1 + n1 <= o2
     assert p.peak >= e + 2000 and a == 0 and c > b
+
+
+def test_half_width_tiles_rule():
+    """Short-K GEMMs whose 128-wide tiles fill at most half the SMs get 64-wide tiles (plan.Planner.wmat); everything else keeps
+    the widest tile (long K: split-K territory; GEGLU; more than half a wave; explicit tile width)."""
+    import math
+    P = plan.Planner()
+    mk = lambda N, K: torch.zeros(N, K)
+    assert P.wmat(mk(640, 640), None, 1, 640, m_rows=1024).bn == 64          # 40 tiles on 148 SMs, 10 k-blocks
+    assert P.wmat(mk(640, 1280), None, 1, 1280, m_rows=1024).bn == 64
+    assert P.wmat(mk(640, 5760), None, 9, 640, m_rows=1024).bn == 128        # long K: left to split-K
+    assert P.wmat(mk(384, 384), None, 1, 384, m_rows=4096).bn == 128         # 96 tiles: halving would need a second wave
+    assert P.wmat(mk(256, 256), None, 1, 256, m_rows=16384).bn == 128
+    assert P.wmat(mk(5120, 640), torch.zeros(5120), 1, 640, geglu=True, m_rows=1024).bn == 128
+    assert P.wmat(mk(640, 640), None, 1, 640, m_rows=1024, bn=128).bn == 128 # explicit width wins
+    assert P.wmat(mk(640, 640), None, 1, 640).bn == 128                      # no row count: no rule
+
+
+def test_groupnorm_scratch_outside_the_pool():
+    """The GroupNorm scratch holds ticket counters that must stay zero between runs: it may not come from the pool's free list
+    (holes there are rewritten by other ops on every run) -- finish() places it above the high-water mark."""
+    P = plan.Planner()
+    a = plan.F32(P.raw(4 * 64 * 128 * 4), 4 * 64, 128)
+    hole = P.raw(1 << 22); P.free(hole)               # a hole large enough for the scratch
+    g, b = P.vec(torch.ones(128)), P.vec(torch.zeros(128))
+    P.prep(_lib.PREP_GN_SILU, a, None, g, b, eps=1e-5, B=4, HW=64)
+    peak_before = P.pool.peak
+    pl = P.finish({})
+    scr = [o["scratch"] for o in pl.ops if o["kind"] == "prep"]
+    assert scr and all(isinstance(r, plan.Ref) and r.region == "ws" and r.off >= peak_before for r in scr)
+    assert pl.ws_bytes >= scr[0].off + 4 * (64 * 32 * 2 * 8 + 32 * 2 * 4 + 4)
