@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       }
       uint8_t* ph = sm + PP + row * 128;
 #pragma unroll
-      for (int c = 0; c < KT / 8; ++c) *reinterpret_cast<uint4*>(ph + (((uint32_t)c ^ swz) << 4)) = pack8_hi(s + c * 8);
+      for (int c = 0; c < KT / 8; ++c) *reinterpret_cast<uint4*>(ph + (((uint32_t)c ^ swz) << 4)) = pack8_hi_unit(s + c * 8);
       fence_proxy_async();          // P (generic-proxy stores) -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
@@ -278,6 +278,245 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         if (!s_next) issue_S(it + 1);
       }
       pdl_launch();     // last P V issued: schedule the next kernel's blocks under this CTA's tail
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Three CTAs per SM (used for Nk <= 512).  The kernel above is a chain of latencies per key tile -- S ready -> TMEM read -> max -> exp ->
+// P stored -> P V -> O read -- with two CTAs per SM to hide them: issue slots 49 % busy, tensor pipe 10 % (profiles/r02_ncu_full.md).
+// A third resident CTA needs <= 113 registers per thread, <= 75 KB of shared memory and <= 170 TMEM columns:
+//   * the scores stay in TENSOR MEMORY and are read twice in 32-column pieces (pass 1: row maximum, pass 2: exp2 + pack), so a
+//     softmax thread holds 32 scores + 32 output accumulators instead of 64 + 32 (+ 32 transient);
+//   * S is single-buffered (columns [0,64); O_tile [64,96); 128 columns allocated): S(it+1) is issued right after the softmax warps
+//     released S(it), ahead of P V(it), so the next tile's scores are ready one short MMA (2 instructions) after the hand-over;
+//   * three K/V stages (68 KB + barriers).
+// Same arithmetic as attention_tc_kernel (the row sum is accumulated per 32-column piece).
+// ------------------------------------------------------------------------------------------------
+namespace atc3 {
+constexpr int QT = 128, KT = 64, NS = 3;
+constexpr int QA = 0;                           // [128][128B]
+constexpr int KB = QA + QT * 128;               // NS x [64][128B]
+constexpr int VT = KB + NS * KT * 128;          // NS x [32][128B]
+constexpr int PP = VT + NS * ATT_D * 128;       // [128][128B]
+constexpr int BAR = PP + QT * 128;
+constexpr int SMEM = BAR + 128 + 1024;
+constexpr int TMEM_COLS = 128;                  // S: cols [0,64); O_tile: cols [64,96)
+}  // namespace atc3
+
+__global__ void __launch_bounds__(192, 3) attention_tc3_kernel(const __grid_constant__ aldm_attn_desc d) {
+  using namespace atc3;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar = base + BAR;
+  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = kv_full0 + 8 * NS, s_full = kv_empty0 + 8 * NS,
+                 p_full = s_full + 8, o_full = p_full + 8, tmem_slot = o_full + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int bkv = d.kv_bmod > 0 ? b % d.kv_bmod : b;
+  const int nt = (d.Nk + KT - 1) / KT;
+
+  if (tid == 0) {
+    mbar_init(q_full, 32);
+    for (int i = 0; i < NS; ++i) { mbar_init(kv_full0 + 8 * i, 32); mbar_init(kv_empty0 + 8 * i, 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+  const uint32_t tmem_S = tmem, tmem_O = tmem + 64;
+  pdl_wait();
+
+  if (warp < 4) {
+    // =============================== softmax + output ===============================
+    const int row = tid, q = q0 + row;
+    const float sl2 = d.scale * 1.4426950408889634f;
+    const uint32_t trow = (uint32_t)(warp * 32) << 16;
+    const uint32_t swz = (uint32_t)(row & 7);
+    float o[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+    float mrun = -INFINITY, lrun = 0.f;
+    const float* mrow = d.mask ? d.mask + (long long)bkv * d.Nk : nullptr;
+    for (int it = 0; it < nt; ++it) {
+      const int k0 = it * KT;
+      const bool interior = k0 + KT <= d.Nk && !mrow;
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum (scores stay in tensor memory) ----
+      float mnew;
+      {
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float s[32];
+          tmem_ld32(tmem_S + trow + hf * 32, reinterpret_cast<uint32_t*>(s));
+          tmem_ld_wait();
+          if (interior) {
+            float t4[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+            for (int j = 4; j < 32; j += 4) {
+              t4[0] = fmaxf(t4[0], s[j]); t4[1] = fmaxf(t4[1], s[j + 1]); t4[2] = fmaxf(t4[2], s[j + 2]); t4[3] = fmaxf(t4[3], s[j + 3]);
+            }
+            tmax = fmaxf(tmax, fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int key = k0 + hf * 32 + j;
+              float v = s[j] * sl2;
+              if (key >= d.Nk) v = -INFINITY;                               // beyond the key range: excluded
+              else if (mrow && __ldg(mrow + key) != 1.0f) v = -FLT_MAX;     // masked_fill(-finfo.max), attention.py:356-360
+              tmax = fmaxf(tmax, v);
+            }
+          }
+        }
+        mnew = fmaxf(mrun, interior ? tmax * sl2 : tmax);      // sl2 > 0
+      }
+      const float corr = (mrun == -INFINITY) ? 0.f : ex2_approx(mrun - mnew);
+      // ---- fold in O_tile of the previous key tile, rescaled to the new maximum (also: P V(it-1) has finished reading P) ----
+      if (it > 0) {
+        mbar_wait(o_full, (it - 1) & 1);
+        tc_fence_after();
+        float ot[ATT_D];
+        tmem_ld32(tmem_O + trow, reinterpret_cast<uint32_t*>(ot));
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < ATT_D; ++i) o[i] = (o[i] + ot[i]) * corr;
+      }
+      // ---- pass 2: probabilities -> fp16 P in shared memory, row sum from the unrounded values ----
+      float psum = 0.f;
+      uint8_t* ph = sm + PP + row * 128;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float s[32];
+        tmem_ld32(tmem_S + trow + hf * 32, reinterpret_cast<uint32_t*>(s));
+        tmem_ld_wait();
+        float p4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (interior) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float p = ex2_approx(fmaf(s[j + e], sl2, -mnew));
+              s[j + e] = p;
+              p4[e] += p;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = k0 + hf * 32 + j;
+            float v = s[j] * sl2;
+            if (key >= d.Nk) v = -INFINITY;
+            else if (mrow && __ldg(mrow + key) != 1.0f) v = -FLT_MAX;
+            const float p = (v == -INFINITY) ? 0.f : ex2_approx(v - mnew);
+            s[j] = p;
+            p4[j & 3] += p;
+          }
+        }
+        psum += (p4[0] + p4[1]) + (p4[2] + p4[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(ph + (((uint32_t)(hf * 4 + c) ^ swz) << 4)) = pack8_hi_unit(s + c * 8);
+      }
+      lrun = lrun * corr + psum;
+      mrun = mnew;
+      fence_proxy_async();          // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+      tc_fence_before();            // our TMEM reads of S are complete before the MMA warp overwrites it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    {
+      mbar_wait(o_full, (nt - 1) & 1);
+      tc_fence_after();
+      float ot[ATT_D];
+      tmem_ld32(tmem_O + trow, reinterpret_cast<uint32_t*>(ot));
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < ATT_D; ++i) o[i] += ot[i];
+    }
+    tc_fence_before();
+    if (q < d.Nq) {
+      const float inv = 1.0f / lrun;
+#pragma unroll
+      for (int i = 0; i < ATT_D; ++i) o[i] *= inv;
+      store_out_row(d, (long long)b * d.Nq + q, h, o);
+    }
+  } else if (warp == 4) {
+    // =============================== loader ===============================
+    const aldm_plane_t* qh = reinterpret_cast<const aldm_plane_t*>(d.q_hi);
+    const aldm_plane_t* kh = reinterpret_cast<const aldm_plane_t*>(d.k_hi);
+    const aldm_plane_t* vh = reinterpret_cast<const aldm_plane_t*>(d.vt_hi);
+    for (int idx = lane; idx < QT * 4; idx += 32) {
+      const int r = idx >> 2, c = idx & 3;
+      const bool ok = q0 + r < d.Nq;
+      const long long off = ok ? ((long long)b * d.Nq + q0 + r) * d.ldq + d.q_col + h * ATT_D + c * 8 : 0;
+      cp_async_16(base + QA + r * 128 + ((uint32_t)(c ^ (r & 7)) << 4), qh + off, ok ? 16u : 0u);
+    }
+    cp_async_mbar_arrive_noinc(q_full);
+    const int ck = lane & 3, rk = lane >> 2;
+    const int cv = lane & 7, rv = lane >> 3;
+    const aldm_plane_t* kcol = kh + (long long)bkv * d.Nk * d.ldk + d.k_col + h * ATT_D + ck * 8;
+    const long long vrow0 = ((long long)(bkv * d.heads + h) * ATT_D + rv) * d.ld_t + cv * 8;
+    const long long kstep = 8ll * d.ldk, vstep = 4ll * d.ld_t;
+    for (int it = 0, s = 0, ph = 1; it < nt; ++it) {
+      const int k0 = it * KT;
+      mbar_wait(kv_empty0 + 8 * s, ph);
+      const uint32_t kb = base + KB + s * (KT * 128);
+      const aldm_plane_t* kp = kcol + (long long)(k0 + rk) * d.ldk;
+#pragma unroll
+      for (int i = 0; i < KT / 8; ++i) {
+        const int r = rk + 8 * i;
+        const bool ok = k0 + r < d.Nk;
+        cp_async_16(kb + r * 128 + ((uint32_t)(ck ^ (r & 7)) << 4), ok ? kp + i * kstep : kcol, ok ? 16u : 0u);
+      }
+      const uint32_t vb = base + VT + s * (ATT_D * 128);
+      const bool vok = k0 + cv * 8 < d.Nk;
+#pragma unroll
+      for (int i = 0; i < ATT_D / 4; ++i) {
+        const int r = rv + 4 * i;
+        const aldm_plane_t* vp = vh + vrow0 + i * vstep + k0;
+        cp_async_16(vb + r * 128 + ((uint32_t)(cv ^ (r & 7)) << 4), vok ? vp : vh, vok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive_noinc(kv_full0 + 8 * s);
+      if (++s == NS) { s = 0; ph ^= 1; }
+    }
+  } else {
+    // =============================== MMA issuer ===============================
+    if (elect_one()) {
+      constexpr uint32_t idS = umma_idesc_f16(128, KT), idO = umma_idesc_f16(128, ATT_D);
+      const uint64_t dQ = umma_desc_sw128(base + QA);
+      const uint64_t dP = umma_desc_sw128(base + PP);
+      auto issue_S = [&](int t) {      // S(t) = Q K(t)^T
+        const int st = t % NS;
+        mbar_wait(kv_full0 + 8 * st, (t / NS) & 1);
+        tc_fence_after();
+        const uint64_t dK = umma_desc_sw128(base + KB + st * (KT * 128));
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) umma_f16(tmem_S, dQ + 2 * ks, dK + 2 * ks, idS, ks > 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_S(0);
+      for (int it = 0; it < nt; ++it) {
+        const int s = it % NS;
+        mbar_wait(p_full, it & 1);         // the softmax warps have read S(it) and written P(it)
+        tc_fence_after();
+        if (it + 1 < nt) issue_S(it + 1);  // scores of the next tile first: the softmax warps wait for nothing else
+        const uint64_t dV = umma_desc_sw128(base + VT + s * (ATT_D * 128));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_O, dP + 2 * ks, dV + 2 * ks, idO, ks > 0);
+        umma_commit(o_full);
+        umma_commit(kv_empty0 + 8 * s);
+      }
+      pdl_launch();
     }
     __syncwarp();
   }
@@ -433,6 +672,16 @@ int attention_launch(const aldm_attn_desc& d, cudaStream_t st) {
     if (d.Nk <= 8) ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<8>, grid, dim3(128), 0, st, d));
     else if (d.Nk <= 16) ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<16>, grid, dim3(128), 0, st, d));
     else ALDM_CHECK_CUDA(launch_pdl(attention_short_kernel<32>, grid, dim3(128), 0, st, d));
+  } else if (d.Nk <= 512 && !(getenv("ALDM_ATTN3") && getenv("ALDM_ATTN3")[0] == '0')) {
+    // three CTAs per SM for up to 8 key tiles (measured: 13.1 vs 15.0 us at N = 256, 6.7 vs 7.9 at N = 64; at N = 1024 the second
+    // TMEM pass and the single S buffer cost more than the third CTA hides: 84.6 vs 80.8 us).  ALDM_ATTN3=0: A/B switch.
+    static bool configured3 = false;
+    if (!configured3) {
+      ALDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, atc3::SMEM));
+      configured3 = true;
+    }
+    dim3 grid(cdiv(d.Nq, atc3::QT), d.heads, d.B);
+    ALDM_CHECK_CUDA(launch_pdl(attention_tc3_kernel, grid, dim3(192), atc3::SMEM, st, d));
   } else {
     static bool configured = false;
     constexpr int NS = 4;       // 81 KB: two CTAs per SM (TMEM: 2 x 256 columns)
