@@ -52,6 +52,10 @@ __device__ __forceinline__ void store_out_row(const aldm_attn_desc& d, long long
 
 namespace atc {
 constexpr int QT = 128, KT = 64;
+// The row sums of P come from the tensor core: V^T carries a 33rd row of ones (N = 48 instead of 32: +8 cycles per instruction),
+// so column 32 of O_tile is sum_k P[q, k] -- of the fp16-ROUNDED probabilities, i.e. exactly the weights the numerator uses.
+// That removes 64 FADD per row and key tile from an instruction-bound loop.
+constexpr int VROWS = 48;
 // NS = number of K/V stages (a stage is released after P V(it), so the prefetch distance is NS - 1 tile periods; the
 // 2-stage kernel of round 1 left the softmax warps waiting for S 43% of the time).  Rows are 128 bytes in the
 // SWIZZLE_128B layout; Q and K use the first 64 bytes of each row (32 dims x fp16), V^T and P all 128 (64 keys).
@@ -59,12 +63,12 @@ template <int NS>
 struct Cfg {
   static constexpr int QA = 0;                           // [128][128B]  q in chunks 0..3
   static constexpr int KB = QA + QT * 128;               // NS x [64][128B]   k in chunks 0..3
-  static constexpr int VT = KB + NS * KT * 128;          // NS x [32][128B]   v^T (64 keys per row)
-  static constexpr int PP = VT + NS * ATT_D * 128;       // [128][128B]       p (64 keys per row)
+  static constexpr int VT = KB + NS * KT * 128;          // NS x [48][128B]   v^T (64 keys per row); row 32 = ones, rows 33..47 = 0
+  static constexpr int PP = VT + NS * VROWS * 128;       // [128][128B]       p (64 keys per row)
   static constexpr int BAR = PP + QT * 128;
   static constexpr int SMEM = BAR + 128 + 1024;          // + barriers + round-up slack for the 1024-byte tile alignment
 };
-constexpr int TMEM_COLS = 256;                 // S double buffer: cols [0,64) / [64,128); O_tile: cols [128,160)
+constexpr int TMEM_COLS = 256;                 // S double buffer: cols [0,64) / [64,128); O_tile: cols [128,176) (32 outputs + row sum + pad)
 }  // namespace atc
 
 template <int NS>
@@ -92,6 +96,13 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 5) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  // rows 32..47 of every V^T stage (written once; the loader only ever overwrites rows 0..31): ones, then zeros
+  for (int i = tid; i < NS * 16 * 8; i += 192) {
+    const int st = i / 128, r = 32 + ((i >> 3) & 15);
+    const uint32_t v = r == 32 ? 0x3C003C00u : 0u;      // fp16 1.0 pairs
+    *reinterpret_cast<uint4*>(sm + VT + st * (VROWS * 128) + r * 128 + ((i & 7) << 4)) = make_uint4(v, v, v, v);
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       tmem_ld32(tmem_S + (it & 1) * KT + trow, reinterpret_cast<uint32_t*>(s));
       tmem_ld32(tmem_S + (it & 1) * KT + trow + 32, reinterpret_cast<uint32_t*>(s + 32));
       tmem_ld_wait();
-      float mnew, corr, psum = 0.f;
+      float mnew, corr;
       if (k0 + KT <= d.Nk && !mrow) {
         // interior tile, no mask: max on the raw scores (sl2 > 0), one FFMA + one MUFU per element
         // four independent max / sum chains: a single chain of 64 dependent operations (4-cycle latency each) left the
@@ -131,17 +142,8 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         const float tmax = fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3]));
         mnew = fmaxf(mrun, tmax * sl2);
         corr = ex2_approx(mrun - mnew);                  // mrun = -inf on the first tile -> 0
-        float p4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < KT; j += 4) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p = ex2_approx(fmaf(s[j + e], sl2, -mnew));
-            s[j + e] = p;
-            p4[e] += p;
-          }
-        }
-        psum = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+        for (int j = 0; j < KT; ++j) s[j] = ex2_approx(fmaf(s[j], sl2, -mnew));
       } else {
         float tmax = -INFINITY;
 #pragma unroll
@@ -157,12 +159,9 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         corr = (mrun == -INFINITY) ? 0.f : ex2_approx(mrun - mnew);
 #pragma unroll
         for (int j = 0; j < KT; ++j) {
-          const float p = (s[j] == -INFINITY) ? 0.f : ex2_approx(s[j] - mnew);
-          s[j] = p;
-          psum += p;
+          s[j] = (s[j] == -INFINITY) ? 0.f : ex2_approx(s[j] - mnew);
         }
       }
-      lrun = lrun * corr + psum;
       mrun = mnew;
       // Deferred accumulation: fold in O_tile of the PREVIOUS key tile (its P V product has long finished
       // while this tile's probabilities were computed), then rescale to the new running maximum.  Waiting
@@ -172,9 +171,11 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         tc_fence_after();
         float ot[ATT_D];
         tmem_ld32(tmem_O + trow, reinterpret_cast<uint32_t*>(ot));
+        const uint32_t lt = tmem_ld1(tmem_O + trow + ATT_D);      // column 32: row sum of P(it-1)
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < ATT_D; ++i) o[i] = (o[i] + ot[i]) * corr;
+        lrun = (lrun + __uint_as_float(lt)) * corr;
       }
       uint8_t* ph = sm + PP + row * 128;
 #pragma unroll
@@ -189,9 +190,11 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       tc_fence_after();
       float ot[ATT_D];
       tmem_ld32(tmem_O + trow, reinterpret_cast<uint32_t*>(ot));
+      const uint32_t lt = tmem_ld1(tmem_O + trow + ATT_D);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < ATT_D; ++i) o[i] += ot[i];
+      lrun += __uint_as_float(lt);
     }
     tc_fence_before();
     if (q < d.Nq) {
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         const bool ok = k0 + r < d.Nk;
         cp_async_16(kb + r * 128 + ((uint32_t)(ck ^ (r & 7)) << 4), ok ? kp + i * kstep : kcol, ok ? 16u : 0u);
       }
-      const uint32_t vb = base + VT + s * (ATT_D * 128);
+      const uint32_t vb = base + VT + s * (VROWS * 128);
       const bool vok = k0 + cv * 8 < d.Nk;
 #pragma unroll
       for (int i = 0; i < ATT_D / 4; ++i) {
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
   } else {
     // =============================== MMA issuer ===============================
     if (elect_one()) {
-      constexpr uint32_t idS = umma_idesc_f16(128, KT), idO = umma_idesc_f16(128, ATT_D);
+      constexpr uint32_t idS = umma_idesc_f16(128, KT), idO = umma_idesc_f16(128, VROWS);
       const uint64_t dQ = umma_desc_sw128(base + QA);
       const uint64_t dP = umma_desc_sw128(base + PP);
       auto issue_S = [&](int t) {      // S(t) = Q K(t)^T into TMEM buffer t & 1
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
         if (!s_next && mbar_test_wait(kv_full0 + 8 * ((it + 1) % NS), ((it + 1) / NS) & 1)) { issue_S(it + 1); s_next = true; }
         mbar_wait(p_full, it & 1);
         tc_fence_after();
-        const uint64_t dV = umma_desc_sw128(base + VT + s * (ATT_D * 128));
+        const uint64_t dV = umma_desc_sw128(base + VT + s * (VROWS * 128));
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_O, dP + 2 * ks, dV + 2 * ks, idO, ks > 0);
         umma_commit(o_full);
