@@ -424,8 +424,113 @@ __global__ void __launch_bounds__(256) gn_apply_col_kernel(const __grid_constant
   pdl_launch();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-pass GroupNorm: one CTA owns ALL rows of a batch element for a chunk of G whole groups (G * cpg >= 32 channels, i.e. row
+// pieces of >= 128 bytes), parks them in shared memory while it reduces the statistics, then normalises out of shared memory.  The
+// tensor is read once instead of twice, one launch instead of two, no scratch, no tickets; deterministic (fixed-order sums).  Used
+// whenever HW x G x cpg x 4 bytes fits (every UNet level except the 4096-pixel one, the VAE mid blocks); the two-kernel path above
+// takes the rest.
+// ---------------------------------------------------------------------------------------------
+static constexpr int GN_FUSED_MAX_SMEM = 200 * 1024;
+
+struct GnFusedPlan {
+  int G, CW, QW, RS;
+  size_t smem;
+  bool ok;
+};
+static GnFusedPlan gn_fused_plan(const aldm_prep_desc& d) {
+  GnFusedPlan p{};
+  const int C = d.c0 + d.c1;
+  if (d.groups != 32 || C % 128 != 0) return p;
+  static const bool on = [] { const char* e = getenv("ALDM_GN_FUSED"); return !(e && e[0] == '0'); }();      // A/B switch
+  if (!on) return p;
+  const int cpg = C / 32;
+  int G = 1;
+  while (G * cpg < 32) G *= 2;
+  p.G = G; p.CW = G * cpg; p.QW = p.CW / 4; p.RS = 256 / p.QW;
+  p.smem = (size_t)d.HW * p.CW * 4;
+  p.ok = G <= 32 && p.QW <= 256 && p.RS >= 1 && p.smem <= (size_t)GN_FUSED_MAX_SMEM && d.HW >= 1;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) gn_fused_kernel(const __grid_constant__ aldm_prep_desc d, int G) {
+  extern __shared__ float4 gn_sx[];                   // [HW][QW]
+  __shared__ float s_a[256], s_a2[256];               // per-thread partials: [slot][q]
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.y;
+  const int C = d.c0 + d.c1, cpg = C / d.groups;
+  const int CW = G * cpg, QW = CW >> 2, RS = 256 / QW;
+  const int c_base = blockIdx.x * CW;
+  const int slot = threadIdx.x / QW, q = threadIdx.x - slot * QW;
+  const bool active = slot < RS;
+  const long long rb = (long long)b * d.HW;
+  pdl_wait();
+  float a = 0.f, a2 = 0.f;
+  if (active) {
+    int r = slot;
+    constexpr int U = 8;        // independent 16-byte loads in flight per thread
+    for (; r + (U - 1) * RS < d.HW; r += U * RS) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = load_cat4(d, rb + r + u * RS, c_base + q * 4);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        gn_sx[(r + u * RS) * QW + q] = v[u];
+        a += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+        a2 = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, fmaf(v[u].w, v[u].w, a2))));
+      }
+    }
+    for (; r < d.HW; r += RS) {
+      const float4 v = load_cat4(d, rb + r, c_base + q * 4);
+      gn_sx[r * QW + q] = v;
+      a += (v.x + v.y) + (v.z + v.w);
+      a2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, a2))));
+    }
+    s_a[slot * QW + q] = a;
+    s_a2[slot * QW + q] = a2;
+  }
+  pdl_launch();
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x, qpg = cpg >> 2;
+    double s = 0.0, s2 = 0.0;
+    for (int sl = 0; sl < RS; ++sl)
+      for (int k = 0; k < qpg; ++k) {
+        s += (double)s_a[sl * QW + g * qpg + k];
+        s2 += (double)s_a2[sl * QW + g * qpg + k];
+      }
+    const double n = (double)d.HW * cpg;
+    const double mean = s / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)d.eps));
+  }
+  __syncthreads();
+  if (!active) return;
+  aldm_plane_t* hi = reinterpret_cast<aldm_plane_t*>(d.out_hi);
+  aldm_plane_t* lo = reinterpret_cast<aldm_plane_t*>(d.out_lo);
+  const bool act = d.mode == ALDM_PREP_GN_SILU;
+  const int g = (q * 4) / cpg;
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(d.gamma + c_base + q * 4));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(d.beta + c_base + q * 4));
+  const float mu = s_mean[g], rs = s_rstd[g];
+  const float sc[4] = {rs * ga.x, rs * ga.y, rs * ga.z, rs * ga.w};
+  const float sh[4] = {be.x - mu * sc[0], be.y - mu * sc[1], be.z - mu * sc[2], be.w - mu * sc[3]};
+  for (int r = slot; r < d.HW; r += RS) {
+    const float4 v = gn_sx[r * QW + q];
+    float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+    if (act) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) y[e] = silu_f(y[e]);
+    }
+    store_planes4(hi, lo, (rb + r) * d.Cp + c_base + q * 4, y);
+  }
+}
+
 int prep_num_launches(const aldm_prep_desc& d) {
-  return (d.mode == ALDM_PREP_GN || d.mode == ALDM_PREP_GN_SILU) ? 2 : 1;      // statistics + apply
+  if (d.mode != ALDM_PREP_GN && d.mode != ALDM_PREP_GN_SILU) return 1;
+  return gn_fused_plan(d).ok ? 1 : 2;      // single-pass kernel, or statistics + apply
 }
 
 int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
@@ -441,7 +546,16 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
     ALDM_REQUIRE(d.rows == d.B * d.HW, ALDM_E_SHAPE, "prep GN: rows != B*HW");
     ALDM_REQUIRE(!d.src_nchw, ALDM_E_UNSUPPORTED, "prep GN: NCHW source");
     const int cpg = C / d.groups;
-    if (cpg % 4 == 0) {
+    const GnFusedPlan fp = gn_fused_plan(d);
+    if (fp.ok) {
+      static bool configured = false;
+      if (!configured) {
+        ALDM_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_FUSED_MAX_SMEM));
+        configured = true;
+      }
+      ALDM_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(32 / fp.G, d.B), dim3(256), fp.smem, st, d, fp.G));
+      ALDM_CHECK_CUDA(cudaGetLastError());
+    } else if (cpg % 4 == 0) {
       // (slot, q) kernels: every thread streams ~8-16 float4 rows; ~4 blocks per SM over the whole batch
       const GnGeom gg = gn_geom(C);
       const int thr = gg.QW * gg.RS;                 // multiple of 32 (Q is a multiple of 32 here), <= 256

@@ -97,10 +97,12 @@ def test_groupnorm_fast_path():
         assert rel_l2(read_gpu_planes(prog, o), em.read_planes(o.hi, o.lo, o.rows, o.Cp)) < 2e-5
 
 
-@pytest.mark.parametrize("B,HW,C", [(2, 4096, 128), (16, 64, 640), (3, 1000, 256), (2, 300, 1280)])
+@pytest.mark.parametrize("B,HW,C", [(2, 4096, 128), (80, 2048, 128), (16, 64, 640), (3, 1000, 256), (2, 300, 1280), (4, 1024, 640)])
 def test_groupnorm_large_and_repeated(B, HW, C):
-    """(slot, q) GroupNorm kernels: many blocks per batch row (statistics published by the last block through the self-resetting
-    ticket) and few (the apply kernel reduces the partials); a second run must see the tickets back at zero."""
+    """GroupNorm kernels.  Single-pass kernel (all rows of a batch element for a chunk of groups parked in shared memory) where
+    HW x chunk fits: (16, 64, 640), (3, 1000, 256), (2, 300, 1280), (4, 1024, 640).  Two-kernel path otherwise: many blocks per
+    batch row (statistics published by the last block through the self-resetting ticket: (2, 4096, 128)) and few (the apply kernel
+    reduces the partials: (80, 2048, 128)); repeated runs must see the tickets back at zero."""
     g = torch.Generator().manual_seed(5)
     P = Planner(keep_plain=True)
     a = F32(P.raw(B * HW * C * 4), B * HW, C)
