@@ -1,10 +1,17 @@
 #!/bin/bash
 # One parameterised GPU job runner (replaces the round-1 one-offs).  Usage (under gpurun, from the repo root):
 #   bash scripts/gpu_run.sh tests            # pytest -m gpu
-#   bash scripts/gpu_run.sh sweep            # ms / DDIM step for lanes x switches (scripts/step_time.py)
-#   bash scripts/gpu_run.sh bench [args...]  # python bench.py args -> gpurun_out/bench_<tag>.json
-#   bash scripts/gpu_run.sh ncu-list         # per-launch times of 2 eager DDIM steps (profiles/*_launches.md source)
-# Several jobs: bash scripts/gpu_run.sh tests sweep bench
+#   bash scripts/gpu_run.sh optests          # tests/test_gpu_ops.py only
+#   bash scripts/gpu_run.sh step             # ms / DDIM step of the default configuration (scripts/step_time.py)
+#   bash scripts/gpu_run.sh sweep            # ms / DDIM step for "lanes:ENV=.. ENV=..;..." configurations in $SWEEP
+#   bash scripts/gpu_run.sh bench            # python bench.py $BENCH_ARGS -> gpurun_out/bench_<tag>.json
+#   bash scripts/gpu_run.sh configs          # BASELINE configs C3 / C4 / C5, one timed batch each
+#   bash scripts/gpu_run.sh ops              # steady-state micro-benchmarks of the dominant op shapes (scripts/prof_ops.py)
+#   bash scripts/gpu_run.sh diag             # the GEMM with its roles switched off ($DIAG_BITS, $DIAG_CASES)
+#   bash scripts/gpu_run.sh micro            # tcgen05.mma issue rates + per-role timelines of CTA 0 ($TL_CASES)
+#   bash scripts/gpu_run.sh ncu-full         # one ncu --set full capture per case in $NCU_CASES -> raw-metric CSVs
+#   bash scripts/gpu_run.sh ncu-list         # per-launch time + DRAM bytes of two DDIM steps (graph kernel nodes)
+# Several jobs: bash scripts/gpu_run.sh tests step bench.  gpurun_out/ is capped at 64 MiB on the way back: no .ncu-rep files in it.
 set +e
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
