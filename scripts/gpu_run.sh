@@ -57,7 +57,7 @@ while [ $# -gt 0 ]; do
     ncu-full)     # one --set full capture per dominant op shape (scripts/prof_ops.py cases) + the small HBM kernels; only the
                   # raw-metric CSV comes back (gpurun_out is capped at 64 MiB: the .ncu-rep files stay on the box)
       for c in ${NCU_CASES:-lin_k1024_n256 lin_k256_n2048_geglu lin_k640_n640 conv_l2_256 attn_1024 ln_16384x256 gn_silu_l1}; do
-        case $c in attn*) pat='attention_tc';; ln*) pat='ln_kernel';; gn*) pat='gn_apply_col';; *) pat='gemm_tc3';; esac
+        case $c in attn*) pat='attention_tc';; ln*) pat='ln_kernel';; gn*) pat='gn_fused|gn_apply_col';; *) pat='gemm_tc3';; esac
         timeout 600 ncu --set full --clock-control none -k regex:$pat -s 1 -c 1 -f -o /tmp/ncu_${TAG}_$c \
           python scripts/prof_ops.py --reps 2 --only $c > gpurun_out/ncu_${TAG}_$c.log 2>&1
         echo "== ncu $c rc=$?"
