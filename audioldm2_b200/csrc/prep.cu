@@ -601,8 +601,6 @@ int prep_launch(const aldm_prep_desc& d, cudaStream_t st) {
   return ALDM_OK;
 }
 
-// partials + (mean, rstd) floats + ticket counters (the tickets must start at zero: the workspace is zero-initialised)
-size_t gn_scratch_doubles(int B) { return (size_t)B * GN_MAX_BLOCKS * 32 * 2 + (size_t)B * 32 + (size_t)(B + 1) / 2; }
 
 // ---------------------------------------------------------------------------------------------
 // pack_b: fp32 [N,K] (or its transpose) -> tile images  [n_tile][k_blk][hi|lo][bn rows][128 B swizzled]
