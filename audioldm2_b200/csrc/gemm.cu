@@ -4,20 +4,21 @@
 //
 // Precision: split-fp16 operands, fp32 accumulation in TMEM.  Weights are packed as two fp16 planes (w ~= hi + lo,
 // 22 significand bits).  Activations arrive as fp16 planes written by the prep kernels / producer epilogues:
-//   * two planes (a_lo != NULL): three kind::f16 UMMAs per K step (lo*hi, hi*lo, hi*hi), ~2^-22 operand precision --
-//     the convolutions, where the 200-step waveform budget goes (scripts/precision_study.py);
-//   * one plane (a_lo == NULL): two UMMAs (hi*lo_w, hi*hi_w) and half the A bytes -- the token-side linear layers.
+//   * two planes (a_lo != NULL): the products hi*hi + hi*lo_w + lo*hi_w, ~2^-22 operand precision, issued as TWO kind::f16
+//     instructions per K step (A_hi against the stage's [W_hi ; W_lo] as one N = 2 BN operand, A_lo against W_hi) -- the
+//     convolutions, where the 200-step waveform budget goes (scripts/precision_study.py);
+//   * one plane (a_lo == NULL): two instructions (hi*lo_w, hi*hi_w) and half the A bytes -- the token-side linear layers.
 // (plain single-pass bf16 / TF32-class rounding of BOTH operands misses or crowds the 1e-3 waveform
 // tolerance; rounding only the activations to 11 bits costs 2e-4 at 200 steps.)
 //
-// Structure of one CTA (192 threads, one 128 x BN output tile, optional split-K slice):
-//   warps 0-3  A producers: gather 16-byte chunks (8 channels of one tap of one pixel) with
-//              cp.async + zero fill into 128B-swizzled K-major tiles; completion is signalled
-//              on the stage's mbarrier (cp.async.mbarrier.arrive).  Afterwards the same warps
-//              run the epilogue (TMEM lane == tile row == threadIdx.x).
-//   warp 4     B producer: one elected lane issues a TMA bulk copy (cp.async.bulk) of the
-//              host-packed, pre-swizzled weight tile image (hi|lo) per stage.
-//   warp 5     allocates TMEM; one elected lane issues tcgen05.mma and commits stages.
+// Structure of one CTA (persistent: 448 threads, one CTA per SM looping over 128 x BN output tiles / split-K slices; details
+// and the measurements behind them at gemm_tc3_kernel below and in DESIGN.md section 4):
+//   warps 0-3   A producers: gather 16-byte chunks (8 channels of one tap of one pixel) with cp.async + zero fill into
+//               128B-swizzled K-major tiles; completion is signalled on the stage's mbarrier (cp.async.mbarrier.arrive).
+//   warp 4      B producer: one ELECTED lane (elect.sync) issues a TMA bulk copy (cp.async.bulk) of the host-packed,
+//               pre-swizzled weight tile image (hi|lo) per stage.
+//   warp 5      allocates TMEM; one elected lane issues tcgen05.mma into a double-buffered accumulator and commits stages.
+//   warps 6-13  epilogue out of TMEM, overlapping the next tile's main loop.
 #include <stdlib.h>
 
 #include "common.cuh"
