@@ -20,6 +20,10 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--mode", default="f16a")
 ap.add_argument("--threads", type=int, default=8)
 ap.add_argument("--only", default="", help="comma list of classes that get rounded: conv,lin,ff,attn,proj (default: all)")
+ap.add_argument("--lnfold", action="store_true",
+                help="LayerNorm folded into its consumer GEMM (DESIGN.md 8.3): the tensor core consumes fp16(x) of the UN-normalised "
+                     "residual stream and the epilogue applies y = rstd (x_h W'^T - mu s) + b', i.e. the consumer sees "
+                     "LN(x) + rstd * gamma * (fp16(x) - x) instead of fp16(LN(x))")
 a = ap.parse_args()
 torch.set_num_threads(a.threads)
 
@@ -42,20 +46,37 @@ def cls_of(n, is_conv):
     if ".attn1." in n or ".attn2." in n: return "lin"
     if "proj_in" in n or "proj_out" in n: return "proj"
     return "conv" if is_conv else "lin"
+LN_CONSUMERS = (".to_q", ".to_k", ".to_v", ".ff.net.0.proj")
 def RA(n, is_conv=False):
+    if a.lnfold and n.endswith(LN_CONSUMERS) and getattr(RA, "from_ln", False):
+        return ident                      # the folded consumer reads fp16(x) itself: its error is injected by _ln below
     return ra if (ONLY is None or cls_of(n, is_conv) in ONLY) else ident
 if ONLY is not None and "attn" not in ONLY: rattn = ident
 
 _conv2d0, _lin0 = OF._conv2d, OF._lin
+_ln0 = OF._ln
+def _ln(sd, n, x):
+    y = _ln0(sd, n, x)
+    if not a.lnfold:
+        return y
+    rstd = torch.rsqrt(x.var(dim=-1, unbiased=False, keepdim=True) + 1e-5)
+    return y + rstd * sd[n + ".weight"] * (r_f16(x) - x)
+OF._ln = _ln
 def _conv2d(sd, n, x, stride=1, padding=0):
     return F.conv2d(RA(n, True)(x), rw(sd[n + ".weight"]), sd.get(n + ".bias"), stride=stride, padding=padding)
 def _lin(sd, n, x):
-    return F.linear(RA(n)(x), rw(sd[n + ".weight"]), sd.get(n + ".bias"))
+    RA.from_ln = n.endswith(".ff.net.0.proj")
+    r = RA(n)
+    RA.from_ln = False
+    return F.linear(r(x), rw(sd[n + ".weight"]), sd.get(n + ".bias"))
 def _cross_attention(sd, n, x, heads, context=None, mask=None):
     ctx = x if context is None else context
+    RA.from_ln = True
     q = F.linear(RA(n + ".to_q")(x), rw(sd[n + ".to_q.weight"]))
+    RA.from_ln = context is None          # K / V of a cross-attention come from the context, not from the LayerNorm
     k = F.linear(RA(n + ".to_k")(ctx), rw(sd[n + ".to_k.weight"]))
     v = F.linear(RA(n + ".to_v")(ctx), rw(sd[n + ".to_v.weight"]))
+    RA.from_ln = False
     b, nq, c = q.shape
     d = c // heads
     def split(t):
