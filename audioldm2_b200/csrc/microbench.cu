@@ -3,6 +3,7 @@
 //   mode 0  SS: A and B from shared memory (what gemm_tc3_kernel issues), N in {32, 64, 128, 256}
 //   mode 1  TS: A from tensor memory, B from shared memory
 //   mode 2  SS with a concurrent shared-memory writer (cp.async-like generic stores from 4 warps) -- operand-port contention
+//   mode 3  TS with the A slice copied smem -> TMEM by tcgen05.cp (128x256b) right before each MMA: what a TS-mode GEMM would pay
 // The operands are whatever the shared / tensor memory holds (the values do not change the timing).
 #include <stdlib.h>
 
@@ -17,6 +18,11 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// smem -> TMEM copy of one 128 x 16 fp16 A slice (128 lanes x 256 bits), executed by the tensor pipe in issue order with the MMAs
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
 }
 
 __global__ void __launch_bounds__(192, 1) umma_rate_kernel(int N, int mode, int reps, long long* out) {
@@ -43,8 +49,14 @@ __global__ void __launch_bounds__(192, 1) umma_rate_kernel(int N, int mode, int 
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint64_t o = (uint64_t)(ks * 2);
-        if ((mode & 3) == 1) umma_f16_ts(tmem, tmem + 256 + ks * 8, db + o, idesc, 1);
-        else umma_f16(tmem, da + o, db + o, idesc, 1);
+        if ((mode & 3) == 1) {
+          umma_f16_ts(tmem, tmem + 256 + ks * 8, db + o, idesc, 1);
+        } else if ((mode & 3) == 3) {      // A staged smem -> TMEM by tcgen05.cp right before the MMA that reads it (two TMEM slots alternate)
+          tmem_cp_128x256b(tmem + 256 + ks * 8, da + o);
+          umma_f16_ts(tmem, tmem + 256 + ks * 8, db + o, idesc, 1);
+        } else {
+          umma_f16(tmem, da + o, db + o, idesc, 1);
+        }
       }
     }
     umma_commit(bar);
@@ -77,7 +89,7 @@ __global__ void __launch_bounds__(192, 1) umma_rate_kernel(int N, int mode, int 
 
 extern "C" int aldm_debug_umma_rate(int32_t N, int32_t mode, int32_t reps, long long* host_out, int32_t n_out) {
   using namespace aldm;
-  ALDM_REQUIRE(host_out && n_out > 0 && reps > 0 && (N == 32 || N == 64 || N == 128 || N == 256) && mode >= 0 && mode <= 6, ALDM_E_ARG,
+  ALDM_REQUIRE(host_out && n_out > 0 && reps > 0 && (N == 32 || N == 64 || N == 128 || N == 256) && mode >= 0 && mode <= 7, ALDM_E_ARG,
                "debug_umma_rate: bad arguments");
   long long* dev = nullptr;
   ALDM_CHECK_CUDA(cudaMalloc(&dev, sizeof(long long) * n_out));

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Cycles per tcgen05.mma (128 x N x 16, fp16, cta_group::1) on one SM, nothing else running on it
-(csrc/microbench.cu).  mode 0 = A, B from shared memory; 1 = A from tensor memory; 2 = SS + concurrent smem writers."""
+(csrc/microbench.cu).  mode 0 = A, B from shared memory; 1 = A from tensor memory; 2 = SS + concurrent smem writers;
+3 = A copied smem -> TMEM by tcgen05.cp before each TS-mode MMA (+4: issuing thread chosen by elect.sync)."""
 import ctypes as C
 import os
 import sys
@@ -15,7 +16,7 @@ L = _lib.lib()
 n_sm = 148
 reps = 2048
 print(f"{'mode':>4s} {'N':>4s} {'cycles/mma (median over SMs)':>30s} {'floor N/2':>10s}")
-for mode in (0, 4, 5, 6):      # bit 2: issuing thread chosen by elect.sync (0: lane == 0, the pre-fix code)
+for mode in (0, 4, 5, 6, 7):   # bit 2: issuing thread chosen by elect.sync (0: lane == 0, the pre-fix code); 7 = tcgen05.cp + TS MMA
     for N in (32, 64, 128, 256):
         buf = (C.c_longlong * n_sm)()
         for _ in range(2):
